@@ -1,0 +1,26 @@
+"""CPU oracle for the solve phase of nabw/poroelasticity-linear-solvers.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package imports this.  Only
+``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl
+reference`` legs of ``bench.py`` may import it, and only as the checker or the
+timed CPU baseline.
+
+PARITY UNPINNED: the reference (pure Python over petsc4py / dolfin / hypre /
+MUMPS) ships no tests, golden vectors or recorded iteration counts, and none
+of its dependencies exist in this image, so the restatement below cannot be
+checked against outputs of the reference itself.  What pins it instead:
+manufactured-solution checks of the assembler, direct-solve cross-checks of
+the Krylov restatements, and the per-function file:line citations.
+
+Modules
+-------
+fem        meshes (dolfin UnitSquareMesh/UnitCubeMesh connectivity), P2^d x P2^d x P1
+           assembly of A, P, P_diff, b (lib/Assembler.py:66-221, :235-270) and
+           DirichletBC.apply (lib/Poromechanics.py:76-83)
+problems   the driver configs (swelling.py, swelling-3d.py, footing.py)
+krylov     PETSc-semantics GMRES / CG / preonly restatements (lib/Solver.py:92-102)
+blockpc    PreconditionerCC.apply 2-way / 3-way (lib/Preconditioner.py:141-250)
+aar        AAR.solve incl. its quirks (lib/AAR.py:46-137)
+anderson   AndersonAcceleration.get_next_vector (lib/AndersonAcceleration.py:19-78)
+amg        CPU restatement of OUR smoothed-aggregation AMG (not hypre)
+"""

@@ -1,0 +1,126 @@
+"""PreconditionerCC.apply restated on scipy blocks (TEST INFRASTRUCTURE).
+
+lib/Preconditioner.py:60-75   sub-matrix extraction (createSubMatrix with is_s/is_f/is_p/is_fp)
+lib/Preconditioner.py:219-246 2-way: y_s = K_s\\x_s ; y_fp = K_fp \\ (x_fp - P_fp,s y_s)
+lib/Preconditioner.py:150-218 3-way: two (p -> f -> s) sweeps, y = w1*y + w2*y_diff
+lib/Preconditioner.py:282-285 flag_3_way = pc type in ('diagonal 3-way','undrained 3-way'), w = (1.0, 0.1)
+lib/Preconditioner.py:102-118 + petsc-options-inexact:78-80  fp block: PCFIELDSPLIT schur / lower /
+                              selfp with split 0 = pressure, split 1 = fluid velocity
+
+Inner solves are injected as callables so the same composition serves the exact config
+(scipy splu standing in for MUMPS, petsc-options-exact:11-35) and the inexact one
+(our CG + smoothed-aggregation AMG, oracle/amg.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from .krylov import InnerKSP
+
+
+def submatrix(M: sp.csr_matrix, rows: np.ndarray, cols: np.ndarray) -> sp.csr_matrix:
+    return M[rows][:, cols].tocsr()
+
+
+class LU:
+    def __init__(self, M):
+        self.lu = spla.splu(sp.csc_matrix(M))
+
+    def __call__(self, x):
+        return self.lu.solve(x)
+
+
+class SchurLowerSelfp:
+    """PCFIELDSPLIT(schur, fact lower, precondition selfp) on the fp block, split 0 = p, split 1 = f.
+
+    y_p = K0 \\ x_p ;  y_f = K1(S_f) \\ (x_f - P_fp y_p),   S_f = P_ff - P_fp diag(P_pp)^-1 P_pf
+    (lib/Preconditioner.py:113-114 adds is_p first, then is_f; petsc-options-inexact:78-80).
+    """
+
+    def __init__(self, Mfp_fp: sp.csr_matrix, nf: int, npp: int, make_k0, make_k1):
+        f = np.arange(nf)
+        p = nf + np.arange(npp)
+        self.nf, self.np_ = nf, npp
+        self.App = submatrix(Mfp_fp, p, p)
+        self.Afp = submatrix(Mfp_fp, f, p)
+        self.Apf = submatrix(Mfp_fp, p, f)
+        self.Aff = submatrix(Mfp_fp, f, f)
+        dinv = sp.diags(1.0 / self.App.diagonal())
+        self.S = (self.Aff - self.Afp @ dinv @ self.Apf).tocsr()
+        self.k0 = make_k0(self.App)
+        self.k1 = make_k1(self.S)
+
+    def __call__(self, x):
+        xf, xp = x[: self.nf], x[self.nf:]
+        yp = self.k0(xp)
+        yf = self.k1(xf - self.Afp @ yp)
+        return np.concatenate([yf, yp])
+
+
+class BlockPC:
+    """y = M^-1 x with the reference's 2-way / 3-way composition."""
+
+    def __init__(self, sys_, solvers: dict, w1=1.0, w2=0.1, anderson=None):
+        """solvers: dict of factories {'s','f','p','fp','diff'}: CSR block -> callable x -> y."""
+        P = sys_.P
+        self.sys = sys_
+        self.three_way = sys_.pc_type in ("diagonal 3-way", "undrained 3-way")
+        s, f, p, fp = sys_.is_s, sys_.is_f, sys_.is_p, sys_.is_fp
+        self.is_s, self.is_f, self.is_p, self.is_fp = s, f, p, fp
+        self.Ms_s = submatrix(P, s, s)
+        self.k_s = solvers["s"](self.Ms_s)
+        self.w1, self.w2 = w1, w2
+        self.anderson = anderson
+        if self.three_way:
+            self.Ms_f, self.Ms_p = submatrix(P, s, f), submatrix(P, s, p)
+            self.Mf_f, self.Mf_p = submatrix(P, f, f), submatrix(P, f, p)
+            self.Mp_p = submatrix(P, p, p)
+            self.Mp_diff = submatrix(sys_.P_diff, p, p)
+            self.k_f = solvers["f"](self.Mf_f)
+            self.k_p = solvers["p"](self.Mp_p)
+            self.k_diff = solvers["diff"](self.Mp_diff)
+            self.bcs_sub_pressure = sys_.bcs_sub_pressure
+        else:
+            self.Mfp_s = submatrix(P, fp, s)
+            self.Mfp_fp = submatrix(P, fp, fp)
+            self.k_fp = solvers["fp"](self.Mfp_fp)
+
+    def __call__(self, x):
+        y = np.zeros_like(x)
+        xs = x[self.is_s]
+        if self.three_way:
+            xf, xp = x[self.is_f], x[self.is_p]
+            yp = self.k_p(xp)                                     # :170
+            xpd = xp.copy()
+            xpd[self.bcs_sub_pressure] = 0.0                      # :172-173
+            ypd = self.k_diff(xpd)                                # :174
+            yf = self.k_f(xf - self.Mf_p @ yp)                    # :180-182
+            yfd = self.k_f(xf - self.Mf_p @ ypd)                  # :184-186
+            ys = self.k_s(xs - (self.Ms_f @ yf + self.Ms_p @ yp))       # :192-196
+            ysd = self.k_s(xs - (self.Ms_f @ yfd + self.Ms_p @ ypd))    # :198-202
+            y[self.is_s] = self.w1 * ys + self.w2 * ysd           # :207-212
+            y[self.is_f] = self.w1 * yf + self.w2 * yfd
+            y[self.is_p] = self.w1 * yp + self.w2 * ypd
+        else:
+            ys = self.k_s(xs)                                     # :221
+            t = x[self.is_fp] - self.Mfp_s @ ys                   # :232-233
+            y[self.is_s] = ys
+            y[self.is_fp] = self.k_fp(t)                          # :234
+        if self.anderson is not None and self.anderson.order > 0:  # :248-249
+            y = self.anderson.get_next_vector(y)
+        return y
+
+
+def exact_solvers():
+    """petsc-options-exact: every inner KSP is preonly + LU."""
+    mk = lambda M: LU(M)
+    return {"s": mk, "f": mk, "p": mk, "fp": mk, "diff": mk}
+
+
+def krylov_solver(ksp_type, make_pc, **opts):
+    """Factory: CSR block -> InnerKSP(ksp_type, pc = make_pc(block))."""
+    def mk(M):
+        return InnerKSP(M, make_pc(M) if make_pc else None, ksp_type, **opts)
+    return mk
