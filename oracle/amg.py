@@ -62,7 +62,7 @@ def strength_graph(A: sp.csr_matrix, bs: int, theta: float):
     N2.sum_duplicates()
     d = N2.diagonal()
     G = N2.tocoo()
-    strong = (G.row != G.col) & (G.data >= theta * theta * d[G.row] * d[G.col]) & (G.data > 0)
+    strong = (G.row != G.col) & (G.data >= theta * theta * np.sqrt(d[G.row] * d[G.col])) & (G.data > 0)
     S = sp.coo_matrix((G.data[strong], (G.row[strong], G.col[strong])), shape=(nn, nn)).tocsr()
     S = S.maximum(S.T).tocsr()
     S.sort_indices()
@@ -81,7 +81,7 @@ def aggregate_mis2(S: sp.csr_matrix):
     """Deterministic MIS(2) aggregation.  Returns (agg (nn,) int, -1 = isolated; n_agg)."""
     nn = S.shape[0]
     deg = np.diff(S.indptr)
-    prio = (hash32(np.arange(nn)) << 32) | np.arange(nn)       # unique key per node, > 0
+    prio = ((hash32(np.arange(nn)) >> 1) << 32) | (np.arange(nn) + 1)   # unique 63-bit key per node, > 0
     UNDEC, IN, OUT = 0, 1, 2
     state = np.where(deg == 0, OUT, UNDEC)
     while (state == UNDEC).any():
@@ -198,7 +198,7 @@ class SAAMG:
             B[dir_rows] = 0.0
             S = strength_graph(A, bs, theta)
             agg, n_agg = aggregate_mis2(S)
-            if n_agg == 0 or n_agg * B.shape[1] >= n:
+            if n_agg == 0 or n_agg * B.shape[1] >= 0.8 * n:
                 break
             T, Bc = tentative_prolongator(agg, n_agg, bs, B)
             omega = 4.0 / (3.0 * L.lmax / 1.1)

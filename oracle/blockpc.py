@@ -124,3 +124,32 @@ def krylov_solver(ksp_type, make_pc, **opts):
     def mk(M):
         return InnerKSP(M, make_pc(M) if make_pc else None, ksp_type, **opts)
     return mk
+
+
+class SchurLower:
+    """General 2-split PCFIELDSPLIT(schur, lower, selfp) on the fp block.
+
+    first='p' is the reference's order (SchurLowerSelfp above); first='f' eliminates the
+    fluid velocity first and puts the Schur complement on the pressure:
+        y_f = K0(P_ff) \\ x_f ;  y_p = K1(S_p) \\ (x_p - P_pf y_f),  S_p = P_pp - P_pf diag(P_ff)^-1 P_fp
+    """
+
+    def __init__(self, Mfp_fp, nf, npp, make_k0, make_k1, first="p"):
+        f = np.arange(nf)
+        p = nf + np.arange(npp)
+        self.nf, self.np_, self.first = nf, npp, first
+        i0, i1 = (p, f) if first == "p" else (f, p)
+        self.A00 = submatrix(Mfp_fp, i0, i0)
+        self.A01 = submatrix(Mfp_fp, i0, i1)
+        self.A10 = submatrix(Mfp_fp, i1, i0)
+        self.A11 = submatrix(Mfp_fp, i1, i1)
+        self.S = (self.A11 - self.A10 @ sp.diags(1.0 / self.A00.diagonal()) @ self.A01).tocsr()
+        self.k0, self.k1 = make_k0(self.A00), make_k1(self.S)
+
+    def __call__(self, x):
+        xf, xp = x[: self.nf], x[self.nf:]
+        x0, x1 = (xp, xf) if self.first == "p" else (xf, xp)
+        y0 = self.k0(x0)
+        y1 = self.k1(x1 - self.A10 @ y0)
+        yf, yp = (y1, y0) if self.first == "p" else (y0, y1)
+        return np.concatenate([yf, yp])

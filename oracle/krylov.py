@@ -46,8 +46,11 @@ def _converged(rnorm, it, state, rtol, atol, dtol):
 
 
 def gmres(A, b, M=None, rtol=1e-5, atol=1e-50, dtol=1e5, max_it=10000, restart=30, pc_side="left",
-          cgs2=False, x0=None) -> KSPResult:
-    """A, M: callables v -> A v, v -> M^-1 v."""
+          cgs2=False, x0=None, flexible=False) -> KSPResult:
+    """A, M: callables v -> A v, v -> M^-1 v.  flexible=True is PETSc's KSPFGMRES (right PC,
+    z_j = M^-1 v_j stored, x = x0 + Z y), the correct choice when M is a nonlinear inner solve."""
+    if flexible:
+        pc_side = "right"
     n = len(b)
     M = M or (lambda v: v)
     x = np.zeros(n) if x0 is None else x0.copy()
@@ -71,6 +74,7 @@ def gmres(A, b, M=None, rtol=1e-5, atol=1e-50, dtol=1e5, max_it=10000, restart=3
             break
         m = restart
         V = np.zeros((m + 1, n))
+        Z = np.zeros((m, n)) if flexible else None
         H = np.zeros((m + 1, m))
         cs, sn = np.zeros(m), np.zeros(m)
         g = np.zeros(m + 1)
@@ -78,7 +82,11 @@ def gmres(A, b, M=None, rtol=1e-5, atol=1e-50, dtol=1e5, max_it=10000, restart=3
         V[0] = r / beta
         j = 0
         while reason == 0 and j < m and its < max_it:
-            w = A(M(V[j])) if right else M(A(V[j]))
+            if flexible:
+                Z[j] = M(V[j])
+                w = A(Z[j])
+            else:
+                w = A(M(V[j])) if right else M(A(V[j]))
             h = V[: j + 1] @ w
             w = w - h @ V[: j + 1]
             if cgs2:
@@ -113,8 +121,11 @@ def gmres(A, b, M=None, rtol=1e-5, atol=1e-50, dtol=1e5, max_it=10000, restart=3
                 reason = CONVERGED_RTOL
         if j > 0:
             y = np.linalg.solve(np.triu(H[:j, :j]), g[:j])
-            dx = y @ V[:j]
-            x = x + (M(dx) if right else dx)
+            if flexible:
+                x = x + y @ Z[:j]
+            else:
+                dx = y @ V[:j]
+                x = x + (M(dx) if right else dx)
         if reason == 0 and its >= max_it:
             reason = DIVERGED_ITS
     return KSPResult(x, its, reason, hist)

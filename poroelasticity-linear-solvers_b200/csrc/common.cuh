@@ -1,0 +1,190 @@
+// common.cuh -- context, device buffers, error handling shared by all translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace poro {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define PORO_CUDA(expr)                                                                          \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            char buf__[512];                                                                     \
+            snprintf(buf__, sizeof buf__, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e__),   \
+                     __FILE__, __LINE__, cudaGetErrorString(e__));                               \
+            throw poro::Error(buf__);                                                            \
+        }                                                                                        \
+    } while (0)
+
+#define PORO_REQUIRE(cond, msg)                                                                  \
+    do {                                                                                         \
+        if (!(cond)) throw poro::Error(std::string(msg) + " [" #cond "]");                       \
+    } while (0)
+
+// ---- device buffer ---------------------------------------------------------------------
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DBuf() = default;
+    explicit DBuf(size_t n_) { alloc(n_); }
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+    DBuf(DBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DBuf& operator=(DBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DBuf() { release(); }
+    void alloc(size_t n_) {
+        release();
+        n = n_;
+        if (n) PORO_CUDA(cudaMalloc(&p, n * sizeof(T)));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void zero(cudaStream_t s) { if (n) PORO_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+// ---- NCCL through dlopen (no link-time dependency; single-GPU runs never touch it) -------
+struct NcclApi;
+
+// ---- halo plan (per field after permutation) -----------------------------------------------
+struct HaloField {
+    // for neighbour k: send owned entries send_idx[send_ptr[k]..send_ptr[k+1]) (field-local index),
+    // receive recv_ptr[k+1]-recv_ptr[k] values into halo[recv_ptr[k]..)
+    std::vector<int64_t> send_ptr, recv_ptr;
+    DBuf<int> send_idx;
+    DBuf<double> send_buf;
+    int64_t n_halo = 0;
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    int rank = 0, nranks = 1;
+    void* comm = nullptr;
+    NcclApi* nccl = nullptr;
+    std::map<std::string, std::string> opts;
+    double* h_pin = nullptr;     // pinned host scratch for scalar read-back
+    double* d_scal = nullptr;    // device scratch for reductions
+    static constexpr int kScal = 1 << 18;   // partials; +8192 doubles of small slots behind it
+    int64_t launches = 0;
+    // distributed layout
+    std::vector<int> neigh;
+    int64_t n_owned_raw = -1;
+    std::vector<int64_t> raw_send_ptr, raw_recv_count;
+    std::vector<int32_t> raw_send_idx;
+
+    bool has_opt(const std::string& k) const { return opts.count(k) != 0; }
+    std::string opt(const std::string& k, const std::string& def) const {
+        auto it = opts.find(k);
+        return it == opts.end() ? def : it->second;
+    }
+    double opt_d(const std::string& k, double def) const {
+        auto it = opts.find(k);
+        return it == opts.end() ? def : atof(it->second.c_str());
+    }
+    int opt_i(const std::string& k, int def) const {
+        auto it = opts.find(k);
+        return it == opts.end() ? def : atoi(it->second.c_str());
+    }
+};
+
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// grid for streaming kernels: a few CTAs per SM, never more than needed
+inline int stream_grid(const Ctx& c, int64_t n, int block, int per_thread = 4, int ctas_per_sm = 8) {
+    int64_t need = (n + (int64_t)block * per_thread - 1) / ((int64_t)block * per_thread);
+    int64_t cap = (int64_t)c.sm_count * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+#define PORO_LAUNCH_CHECK(ctx) do { (ctx).launches++; PORO_CUDA(cudaGetLastError()); } while (0)
+
+// ---- sparse matrix (device CSR, local rows) ---------------------------------------------------
+struct Csr {
+    int nrows = 0, ncols = 0;
+    int64_t nnz = 0;
+    DBuf<int> rowptr;      // nrows+1 (nnz < 2^31 per local matrix, checked at creation)
+    DBuf<int> col;
+    DBuf<double> val;
+    int lanes = 0;         // lanes per row chosen for SpMV
+    double avg_row() const { return nrows ? (double)nnz / nrows : 0.0; }
+};
+
+// ---- vec.cu ---------------------------------------------------------------------------------
+void vec_copy(Ctx& c, double* y, const double* x, int64_t n);
+void vec_set(Ctx& c, double* y, double a, int64_t n);
+void vec_scale(Ctx& c, double* y, double a, int64_t n);
+void vec_axpy(Ctx& c, double* y, double a, const double* x, int64_t n);             // y += a x
+void vec_aypx(Ctx& c, double* y, double a, const double* x, int64_t n);             // y = x + a y
+void vec_axpby(Ctx& c, double* y, double a, const double* x, double b, int64_t n);  // y = a x + b y
+void vec_waxpby(Ctx& c, double* w, double a, const double* x, double b, const double* y, int64_t n);
+void vec_pmult(Ctx& c, double* w, const double* d, const double* x, int64_t n);     // w = d .* x
+void vec_gather(Ctx& c, double* y, const double* x, const int* idx, int64_t n);     // y[i] = x[idx[i]]
+void vec_scatter(Ctx& c, double* y, const double* x, const int* idx, int64_t n);    // y[idx[i]] = x[i]
+void vec_set_idx(Ctx& c, double* y, const int* idx, double a, int64_t n);           // y[idx[i]] = a
+// reductions: results land in device memory `d_out` (k doubles), local to this rank
+void vec_dots(Ctx& c, int k, const double* const* xs, const double* const* ys, int64_t n, double* d_out);
+// h[j] = V_j . w for j < ncol (V column-major with leading dimension ld), optional extra ww = w.w at h[ncol]
+void vec_mdot(Ctx& c, const double* V, int64_t ld, int ncol, const double* w, int64_t n, double* d_h, bool with_ww);
+// w -= V h (h device, ncol entries); d_nrm2 (device, 1 double) receives ||w_new||^2 (local)
+void vec_maxpy_norm(Ctx& c, double* w, const double* V, int64_t ld, int ncol, const double* d_h, int64_t n, double* d_nrm2);
+// y += V h with host coefficients (solution update)
+void vec_maxpy_host(Ctx& c, double* y, const double* V, int64_t ld, int ncol, const double* h_host, int64_t n);
+// sum over ranks in place (no-op on one rank), then copy to host and synchronise
+void allreduce_sum(Ctx& c, double* d_vals, int k);
+void fetch(Ctx& c, const double* d_vals, int k, double* host);
+double dot_host(Ctx& c, const double* x, const double* y, int64_t n);   // allreduced, synchronous
+double norm2_host(Ctx& c, const double* x, int64_t n);
+
+// ---- spmv.cu --------------------------------------------------------------------------------
+enum SpmvMode { SPMV_SET = 0, SPMV_SUB = 1, SPMV_ADD = 2 };   // y = Ax | y = z - Ax | y = z + Ax
+void csr_choose_lanes(Csr& A);
+void spmv(Ctx& c, const Csr& A, const double* x, double* y, SpmvMode mode = SPMV_SET, const double* z = nullptr);
+// fused Chebyshev step: t = A d_old; r -= t; d_new = c1 d_old + c2 dinv.*r; x += d_new
+void spmv_cheb_step(Ctx& c, const Csr& A, const double* d_old, double* d_new, double* r, double* x,
+                    const double* dinv, double c1, double c2);
+// w = A p and *d_dot += p . w (local partial; d_dot must be zeroed by caller)
+void spmv_dot(Ctx& c, const Csr& A, const double* p, double* w, double* d_dot);
+
+// ---- setup.cu (device sparse set-up primitives) ----------------------------------------------------
+enum CombineOp { COMBINE_SUM = 0, COMBINE_MAX = 1 };
+// unsorted (key = row<<32 | col, val) with duplicates -> CSR with sorted unique columns. keys/vals are consumed.
+void coo_to_csr(Ctx& c, int nrows, int ncols, int64_t nent, DBuf<uint64_t>& keys, DBuf<double>& vals, Csr& out,
+                CombineOp op = COMBINE_SUM);
+void csr_spgemm(Ctx& c, const Csr& A, const Csr& B, Csr& C);            // C = A B
+void csr_transpose(Ctx& c, const Csr& A, Csr& At);
+// C = A[rows, cols] with maps old index -> new index (or -1 to drop); new sizes given
+void csr_extract(Ctx& c, const Csr& A, const int* row_map, const int* col_map, int new_rows, int new_cols, Csr& C);
+void csr_diag(Ctx& c, const Csr& A, double* d);                          // missing diagonal -> 0
+void csr_copy(Ctx& c, const Csr& A, Csr& B);
+// C = A + alpha * diag(s) * B  (s may be null)
+void csr_add_scaled(Ctx& c, const Csr& A, const Csr& B, double alpha, const double* s, Csr& C);
+void csr_scale_cols(Ctx& c, Csr& A, const double* s);                    // A = A diag(s)
+void csr_to_host(const Csr& A, std::vector<int>& rp, std::vector<int>& ci, std::vector<double>& v);
+void csr_from_host(Ctx& c, int nrows, int ncols, const int64_t* rp, const int* ci, const double* v, Csr& out);
+// dense n x n inverse of a CSR matrix by Gauss-Jordan with partial pivoting (row-major result)
+void dense_inverse(Ctx& c, const Csr& A, DBuf<double>& inv);
+void dense_gemv(Ctx& c, const double* M, int n, const double* x, double* y);
+
+}  // namespace poro

@@ -1,0 +1,106 @@
+"""GPU parity tests: the CUDA path (through ctypes and the C ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+from helpers import AMG_OPTIONS, EXACT_OPTIONS, gpu_solve, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_exact(sys_, par, solver_type="gmres"):
+    from oracle.aar import AAR
+    from oracle.blockpc import BlockPC, exact_solvers
+    from oracle.krylov import gmres
+    A = lambda v: sys_.A @ v
+    pc = BlockPC(sys_, exact_solvers())
+    if solver_type == "aar":
+        s = AAR(par["AAR order"], par["AAR p"], par["AAR omega"], par["AAR beta"], A, pc, atol=par["solver atol"],
+                rtol=par["solver rtol"], maxiter=par["solver maxiter"])
+        x = s.solve(sys_.b)
+        return x, s.it, s.history
+    r = gmres(A, sys_.b, pc, rtol=par["solver rtol"], atol=par["solver atol"], dtol=1e20, max_it=par["solver maxiter"],
+              restart=par["solver maxiter"], pc_side="right")
+    return r.x, r.its, r.history
+
+
+@pytest.mark.parametrize("dim,N", [(2, 10), (3, 3)])
+def test_spmv_matches_scipy(gpu_ctx, dim, N):
+    import torch
+    from oracle.problems import swelling
+    from poro_b200.lib.backend import DeviceMatrix, DeviceVector
+    sys_, _ = swelling(dim, N)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(sys_.n)
+    dA = DeviceMatrix(sys_.A, gpu_ctx)
+    dx, dy = DeviceVector(x, ctx=gpu_ctx), DeviceVector(n=sys_.n, ctx=gpu_ctx)
+    dA.mult(dx, dy)
+    gpu_ctx.sync()
+    y = sys_.A @ x
+    # fp64, different summation order only
+    assert rel(dy.numpy(), y) <= 1e-14
+
+
+@pytest.mark.parametrize("dim,N,pc_type", [(2, 10, "diagonal"), (2, 10, "diagonal 3-way"), (2, 10, "undrained"),
+                                           (3, 3, "diagonal"), (3, 3, "diagonal 3-way")])
+def test_gmres_exact_blocks_matches_oracle(gpu_ctx, dim, N, pc_type):
+    """petsc-options-exact semantics: same iteration count (+-0) and solution as the oracle."""
+    from oracle.problems import swelling
+    sys_, par = swelling(dim, N, pc_type)
+    xo, its_o, hist_o = _oracle_exact(sys_, par)
+    g = gpu_solve(sys_, par, EXACT_OPTIONS)
+    assert g["its"] == its_o
+    assert g["reason"] in (2, 3)
+    np.testing.assert_allclose(g["history"], hist_o, rtol=1e-6, atol=1e-14)
+    assert rel(g["x"], xo) <= 1e-8
+
+
+def test_gmres_exact_with_shuffled_numbering(gpu_ctx):
+    """The library's field permutation: a randomly renumbered system gives the same answer."""
+    from oracle.problems import swelling
+    sys_, par = swelling(2, 10, "diagonal")
+    xo, its_o, _ = _oracle_exact(sys_, par)
+    perm = np.random.default_rng(1).permutation(sys_.n)
+    g = gpu_solve(sys_, par, EXACT_OPTIONS, perm=perm)
+    assert g["its"] == its_o
+    assert rel(g["x"], xo) <= 1e-8
+
+
+@pytest.mark.parametrize("pc_type", ["diagonal", "diagonal 3-way"])
+def test_aar_exact_blocks_matches_oracle(gpu_ctx, pc_type):
+    """swelling.py --solver-type aar (config 2): AAR with its quirks, Gram least squares."""
+    from oracle.problems import swelling
+    sys_, par = swelling(2, 10, pc_type)
+    xo, its_o, hist_o = _oracle_exact(sys_, par, "aar")
+    g = gpu_solve(sys_, par, EXACT_OPTIONS, solver_type="aar")
+    xd = spla.spsolve(sys_.A.tocsc(), sys_.b)
+    assert abs(g["its"] - its_o) <= max(2, its_o // 10)
+    assert rel(g["x"], xd) <= 1e-6
+    # the first iterations are pure Richardson and must agree to rounding
+    np.testing.assert_allclose(g["history"][:4], hist_o[:4], rtol=1e-8)
+
+
+@pytest.mark.parametrize("dim,N", [(2, 20), (3, 6)])
+def test_gmres_amg_solution_and_counts(gpu_ctx, dim, N):
+    """AMG-preconditioned config: solution within 1e-8 of a direct solve, true residual below
+    tolerance, iteration count within 10% of the oracle running the SAME algorithm on CPU."""
+    from oracle.amg import SAAMG, rigid_body_modes
+    from oracle.blockpc import BlockPC, SchurLower, krylov_solver
+    from oracle.krylov import gmres
+    from oracle.problems import swelling
+    sys_, par = swelling(dim, N, "diagonal")
+    par = dict(par)
+    par.update({"solver rtol": 1e-10, "solver atol": 0.0, "solver maxiter": 100})
+    B = rigid_body_modes(sys_.coords_s, dim)
+    amg_v = lambda M: SAAMG(M, dim, B)
+    amg_p = lambda M: SAAMG(M, 1, None)
+    mkfp = lambda M: SchurLower(M, sys_.nf, sys_.np_, krylov_solver("preonly", amg_v), krylov_solver("preonly", amg_p), "f")
+    pc = BlockPC(sys_, {"s": krylov_solver("preonly", amg_v), "fp": mkfp})
+    ro = gmres(lambda v: sys_.A @ v, sys_.b, pc, rtol=1e-10, atol=0.0, dtol=1e20, max_it=100, restart=100, pc_side="right")
+    g = gpu_solve(sys_, par, AMG_OPTIONS)
+    xd = spla.spsolve(sys_.A.tocsc(), sys_.b)
+    assert g["reason"] == 2
+    assert abs(g["its"] - ro.its) <= max(1, int(round(0.1 * ro.its)))
+    res = np.linalg.norm(sys_.b - sys_.A @ g["x"]) / np.linalg.norm(sys_.b)
+    assert res <= 2e-10
+    assert rel(g["x"], xd) <= 1e-8
