@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- 3D swelling (swelling-3d.py) solve phase on B200: time-to-1e-8, GMRES iteration
+throughput, SpMV HBM roofline.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--mesh-n M]
+
+A "step" is ONE complete `Solver.solve(b, x)` of the assembled three-field system from a zero
+initial guess to relative residual 1e-8 (right-preconditioned GMRES + block `diagonal`
+preconditioner with SA-AMG V-cycles, pressure Schur complement) -- set-up (assembly, upload,
+AMG hierarchy) is outside the timed region exactly as the reference times only `ksp.solve`
+(lib/Solver.py:148-152).  `value` = DoFs x outer iterations / second over the K timed steps
+(whole job, all ranks); `e2e` is the same through the host-buffer entry point
+(poro_ksp_solve_host: b copied H2D and x copied D2H inside the timed region).
+
+Weak scaling: N GPUs solve the cube with ~N x the DoFs of the 1-GPU mesh, row-partitioned in
+z-slabs (one rank per GPU, NCCL halo exchange + all-reduce).
+
+`--impl reference`: the reference's own stack (petsc4py/dolfin/hypre) is absent from this image
+and unbuildable offline, so the reference arm times the CPU oracle port (numpy/scipy restatement
+of the same algorithm, oracle/) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BENCH_OPTIONS = """
+-global_ksp_type gmres
+-global_ksp_pc_side right
+-s_ksp_type preonly
+-s_pc_type hypre
+-fp_ksp_type preonly
+-fp_pc_fieldsplit_type schur
+-fp_pc_fieldsplit_schur_fact_type lower
+-fp_pc_fieldsplit_schur_precondition selfp
+-fp_pc_fieldsplit_order fp
+-fp_fieldsplit_0_ksp_type preonly
+-fp_fieldsplit_0_pc_type hypre
+-fp_fieldsplit_1_ksp_type preonly
+-fp_fieldsplit_1_pc_type hypre
+"""
+RTOL = 1e-8
+METRIC = "3D swelling GMRES throughput to rtol 1e-8 (DoFs x outer iterations per second)"
+UNIT = "DoF*it/s"
+
+
+def mesh_for_gpus(base_n: int, gpus: int) -> int:
+    """Weak scaling: cube side so that DoFs ~ gpus x DoFs(base_n)."""
+    return int(round(base_n * gpus ** (1.0 / 3.0)))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks and throttle reasons during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device: int):
+        self.device, self.samples, self.stop_flag, self.th = device, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def oracle_solver(sys_, par, max_it):
+    """The CPU port of the benchmarked algorithm (same options as BENCH_OPTIONS)."""
+    from oracle.amg import SAAMG, rigid_body_modes
+    from oracle.blockpc import BlockPC, SchurLower, krylov_solver
+    from oracle.krylov import gmres
+    dim = sys_.dim
+    B = rigid_body_modes(sys_.coords_s, dim)
+    amg_v = lambda M: SAAMG(M, dim, B)
+    amg_p = lambda M: SAAMG(M, 1, None)
+    mkfp = lambda M: SchurLower(M, sys_.nf, sys_.np_, krylov_solver("preonly", amg_v), krylov_solver("preonly", amg_p), "f")
+    pc = BlockPC(sys_, {"s": krylov_solver("preonly", amg_v), "fp": mkfp})
+    A = sys_.A
+
+    def run():
+        return gmres(lambda v: A @ v, sys_.b, pc, rtol=RTOL, atol=0.0, dtol=1e20, max_it=max_it, restart=max(max_it, 1),
+                     pc_side="right")
+    return run
+
+
+def cpu_baseline(sample_n: int, budget_s: float = 20.0):
+    """Oracle port timed on the host cores on a bounded sample: the same problem on a smaller
+    mesh (the metric is normalised per DoF x iteration)."""
+    from oracle.problems import swelling
+    sys_, par = swelling(3, sample_n, "diagonal")
+    run = oracle_solver(sys_, par, 100)
+    t0 = time.perf_counter()
+    r = run()
+    dt = time.perf_counter() - t0
+    reps = 1
+    while dt < budget_s / 4 and reps < 8:
+        t0 = time.perf_counter()
+        r = run()
+        dt = min(dt, time.perf_counter() - t0)
+        reps += 1
+    return {"value": sys_.n * r.its / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "same problem on mesh N=%d (%d DoFs), full solve to rtol 1e-8: %d its in %.2f s, "
+                      "numpy/scipy single thread; NOT PETSc/hypre" % (sample_n, sys_.n, r.its, dt),
+            "its": r.its, "seconds": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.problems import swelling
+    sample_n = args.cpu_sample_n
+    sys_, par = swelling(3, sample_n, "diagonal")
+    run = oracle_solver(sys_, par, 100)
+    for _ in range(min(args.warmup, 1)):
+        run()
+    t0 = time.perf_counter()
+    its = 0
+    for _ in range(args.steps):
+        its += run().its
+    dt = time.perf_counter() - t0
+    val = sys_.n * its / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "swelling-3d.py, GMRES(right) + block diagonal PC + SA-AMG, rtol 1e-8; CPU oracle port "
+                                   "on a bounded sample mesh N=%d (%d DoFs)" % (sample_n, sys_.n)},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": "mesh N=%d (%d DoFs), %d full solves" % (sample_n, sys_.n, args.steps)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--mesh-n", type=int, default=34, help="cells per side at 1 GPU (swelling-3d.py -N)")
+    ap.add_argument("--cpu-sample-n", type=int, default=12)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    from poro_b200.lib.backend import DeviceMatrix, DeviceVector, get_context
+    from poro_b200.lib.IndexSet import IndexSet
+    from poro_b200.lib.Parser import load_petsc_options
+    from poro_b200.lib.Preconditioner import Preconditioner
+    from poro_b200.lib.Solver import Solver
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = get_context(local_rank)
+    load_petsc_options(ctx, BENCH_OPTIONS, is_text=True)
+
+    # ---- set-up (untimed): assemble on the host, upload, build the preconditioner
+    t_asm = time.perf_counter()
+    N = mesh_for_gpus(args.mesh_n, world)
+    if world > 1:
+        from poro_b200.partition import distributed_problem
+        prob = distributed_problem(3, N, "diagonal", rank, world, ctx)
+        sys_, par, n_global = prob.sys, prob.par, prob.n_global
+    else:
+        from oracle.problems import swelling      # host assembler = test infrastructure standing in for FEniCS
+        sys_, par = swelling(3, N, "diagonal")
+        n_global = sys_.n
+    t_asm = time.perf_counter() - t_asm
+    par = dict(par)
+    par.update({"solver rtol": RTOL, "solver atol": 0.0, "solver maxiter": 100, "solver type": "gmres"})
+    t_set = time.perf_counter()
+    imap = IndexSet(sys_.is_s, sys_.is_f, sys_.is_p, two_way=True, block_dim=3, coords_s=sys_.coords_s,
+                    coords_p=sys_.coords_p) if world == 1 else prob.index_set()
+    dA, dP = DeviceMatrix(sys_.A, ctx), DeviceMatrix(sys_.P, ctx)
+    nnzA = sys_.A.nnz
+    b_host = torch.from_numpy(np.ascontiguousarray(sys_.b)).pin_memory()
+    x_host = torch.zeros_like(b_host).pin_memory()
+    db = DeviceVector(sys_.b, ctx=ctx)
+    dx = DeviceVector(n=len(sys_.b), ctx=ctx)
+    pcw = Preconditioner(imap, dA, dP, None, par, sys_.bcs_sub_pressure)
+    pc = pcw.get_pc()
+    solver = Solver(dA, db, pc, par, imap)
+    solver.create_solver(dA, db, pc)
+    ksp = solver.solver
+    ctx.sync()
+    t_set = time.perf_counter() - t_set
+    A_host, b_np = sys_.A, sys_.b
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.sync()
+
+    def timed(fn, steps):
+        barrier()
+        t0 = time.perf_counter()
+        its = 0
+        for _ in range(steps):
+            its += fn()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt, its
+
+    def step_dev():
+        ksp.solve(db, dx)
+        return ksp.its
+
+    def step_host():
+        ksp.solve_host(b_host, x_host)
+        return ksp.its
+
+    for _ in range(args.warmup):
+        step_dev()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ksp.profile(1)
+    l0 = ctx.launch_count()
+    dt, its = timed(step_dev, args.steps)
+    launches = ctx.launch_count() - l0
+    op_ms, op_calls, op_bytes = ksp.profile(0)
+    clocks = sampler.stop()
+    reason, rnorm = ksp.reason, ksp.rnorm
+    for _ in range(1):
+        step_host()
+    dt_e, its_e = timed(step_host, args.steps)
+
+    # ---- verification of the timed result (outside the timed region)
+    xs = dx.numpy()
+    true_res = None
+    if world == 1:
+        true_res = float(np.linalg.norm(b_np - A_host @ xs) / np.linalg.norm(b_np))
+
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    achieved = (op_bytes / 1e9) / (op_ms / 1e3 / max(op_calls, 1)) if op_calls else None
+    stats = pc.getPythonContext().stats()
+    line = {
+        "metric": METRIC, "value": n_global * its / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "swelling-3d.py -N %d (%d DoFs, nnz(A)=%d on rank 0), GMRES(right, restart=maxiter=100) + "
+                               "block 'diagonal' 2-way PC, SA-AMG V-cycle per block, pressure Schur (selfp), rtol 1e-8, "
+                               "zero initial guess" % (N, n_global, nnzA),
+                   "l2": "inputs larger than L2 (matrix streams >> 126 MB); no explicit flush",
+                   "parallelism": "z-slab row partition x%d" % world if world > 1 else "single GPU"},
+        "time_to_1e-8_s": dt / args.steps, "its_per_solve": its / args.steps, "its_per_s": its / dt,
+        "reason": reason, "rnorm": rnorm, "true_rel_residual": true_res,
+        "setup_s": {"assembly_host": t_asm, "upload_and_pc_setup": t_set},
+        "inner": {k: v for k, v in stats.items() if k.startswith("its_") or k.startswith("calls_")},
+        "e2e": {"value": n_global * its_e / dt_e, "unit": UNIT, "h2d_bytes_per_step": int(b_host.numel() * 8),
+                "d2h_bytes_per_step": int(x_host.numel() * 8), "ms_per_step": 1e3 * dt_e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_spmv<32,SET> (outer operator y = A x)", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "peak_source": peak_src, "bytes_per_launch": op_bytes, "launches_timed": op_calls,
+                     "avg_launch_ms": op_ms / max(op_calls, 1), "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(args.cpu_sample_n)
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -121,10 +121,17 @@ int poro_aar_destroy(poro_aar* aar);
 /* ---- micro-benchmark / introspection entry points ----------------------------------------- */
 /* block names: "A" (whole permuted operator), "ss","sf","sp","fs","ff","fp","ps","pf","pp" of P */
 int poro_pc_block_info(poro_pc* pc, const char* name, int64_t* nrows, int64_t* ncols, int64_t* nnz);
+/* copy a block to host CSR arrays sized from poro_pc_block_info (tests: createSubMatrix parity) */
+int poro_pc_block_copy(poro_pc* pc, const char* name, int64_t* rowptr, int32_t* col, double* val);
 /* one application of the inner solver of a block: "s","f","p","fp","diff" (z = K \ r) */
 int poro_pc_inner_solve(poro_pc* pc, const char* name, const double* r_dev, double* z_dev);
 /* AMG hierarchy of a block's inner PC: per level rows and nnz; returns number of levels */
 int poro_pc_amg_info(poro_pc* pc, const char* name, int64_t* rows, int64_t* nnz, int cap, int* nlevels);
+/* live profile of the outer operator product (the dominant SpMV): CUDA events recorded on the
+ * launching stream around every y = A x inside poro_ksp_solve.  enable = 1 resets and starts,
+ * 0 stops, -1 only reads.  op_bytes = algorithmic bytes of one product
+ * (12 nnz + 4 (nrows+1) + 8 nrows + 8 ncols). */
+int poro_ksp_profile(poro_ksp* ksp, int enable, double* op_ms, int64_t* op_calls, int64_t* op_bytes);
 /* operator y = A x in the solver's internal (field-major) ordering incl. halo exchange */
 int poro_ksp_mult(poro_ksp* ksp, const double* x_dev, double* y_dev);
 

@@ -12,6 +12,7 @@
 #include "amg.cuh"
 #include <cub/cub.cuh>
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 
 namespace poro {
@@ -321,6 +322,20 @@ static void make_dinv(Ctx& c, const Csr& A, DBuf<double>& dinv) {
     pfor(c, A.nrows, [=] __device__(int64_t i) { d[i] = d[i] != 0.0 ? 1.0 / d[i] : 1.0; });
 }
 
+struct Tick {
+    Ctx& c; bool on; const char* what; std::chrono::steady_clock::time_point t0;
+    Tick(Ctx& c_, const char* w) : c(c_), on(c_.has_opt("-poro_verbose")), what(w) {
+        if (on) { cudaStreamSynchronize(c.stream); t0 = std::chrono::steady_clock::now(); }
+    }
+    ~Tick() {
+        if (on) {
+            cudaStreamSynchronize(c.stream);
+            fprintf(stderr, "      [amg] %-22s %8.1f ms\n", what,
+                    1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+        }
+    }
+};
+
 // ---- set-up ---------------------------------------------------------------------------------
 void Amg::setup(Ctx& c, const Csr& A, int bs, const double* B_dev, int k, const AmgParams& p) {
     ctx = &c;
@@ -349,7 +364,8 @@ void Amg::setup(Ctx& c, const Csr& A, int bs, const double* B_dev, int k, const 
         Lp->bs = bs;
         n = Acur->nrows;
         make_dinv(c, *Acur, Lp->dinv);
-        Lp->lmax = 1.1 * power_lmax(c, *Acur, Lp->dinv.p, par.power_its);
+        { Tick t(c, "power iteration"); Lp->lmax = 1.1 * power_lmax(c, *Acur, Lp->dinv.p, par.power_its); }
+        if (c.has_opt("-poro_verbose")) fprintf(stderr, "    [amg] level %d: n=%d nnz=%lld bs=%d lmax=%.4f\n", (int)levels.size() - 1, n, (long long)Acur->nnz, bs, Lp->lmax);
         Lp->x.alloc(n); Lp->b.alloc(n); Lp->r.alloc(n); Lp->d0.alloc(n); Lp->d1.alloc(n);
         if (n <= par.coarse_size || (int)levels.size() >= par.max_levels) break;
         // Dirichlet rows (diagonal only) carry no near-nullspace
@@ -363,25 +379,26 @@ void Amg::setup(Ctx& c, const Csr& A, int bs, const double* B_dev, int k, const 
             });
         }
         Csr S;
-        strength_graph(c, *Acur, bs, par.theta, S);
+        { Tick t(c, "strength graph"); strength_graph(c, *Acur, bs, par.theta, S); }
         DBuf<int> agg;
-        int n_agg = aggregate_mis2(c, S, agg);
+        int n_agg;
+        { Tick t(c, "MIS(2) aggregation"); n_agg = aggregate_mis2(c, S, agg); }
         if (n_agg == 0 || (double)n_agg * k >= 0.8 * n) break;
         Csr T;
         DBuf<double> Bc;
-        tentative(c, agg, n_agg, n / bs, bs, k, B.p, T, Bc);
+        { Tick t(c, "tentative prolongator"); tentative(c, agg, n_agg, n / bs, bs, k, B.p, T, Bc); }
         double omega = 4.0 / (3.0 * Lp->lmax / 1.1);
         {
             Csr AT;
-            csr_spgemm(c, *Acur, T, AT);
+            { Tick t(c, "spgemm A*T"); csr_spgemm(c, *Acur, T, AT); }
             csr_add_scaled(c, T, AT, -omega, Lp->dinv.p, Lp->P);
         }
-        csr_transpose(c, Lp->P, Lp->R);
+        { Tick t(c, "transpose P"); csr_transpose(c, Lp->P, Lp->R); }
         Csr Ac;
         {
             Csr AP;
-            csr_spgemm(c, *Acur, Lp->P, AP);
-            csr_spgemm(c, Lp->R, AP, Ac);
+            { Tick t(c, "spgemm A*P"); csr_spgemm(c, *Acur, Lp->P, AP); }
+            { Tick t(c, "spgemm R*(AP)"); csr_spgemm(c, Lp->R, AP, Ac); }
         }
         // dead coarse dofs (rank-deficient aggregates): unit diagonal
         {
@@ -399,7 +416,7 @@ void Amg::setup(Ctx& c, const Csr& A, int bs, const double* B_dev, int k, const 
     // coarsest level: dense inverse when small enough
     const Csr& Ac = op((int)levels.size() - 1);
     coarse_direct = Ac.nrows <= c.opt_i("poro_amg_dense_limit", 4096);
-    if (coarse_direct) dense_inverse(c, Ac, coarse_inv);
+    if (coarse_direct) { Tick t(c, "dense coarse inverse"); dense_inverse(c, Ac, coarse_inv); }
     PORO_CUDA(cudaStreamSynchronize(c.stream));
 }
 

@@ -72,7 +72,10 @@ int poro_ctx_create(int device, poro_ctx** out) {
     cudaDeviceProp prop;
     PORO_CUDA(cudaGetDeviceProperties(&prop, device));
     c.sm_count = prop.multiProcessorCount;
-    PORO_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    // a BLOCKING stream on purpose: it orders itself against the legacy default stream, i.e. against
+    // plain cudaMemcpy calls in the set-up code and against torch's default-stream work on the buffers
+    // handed across the ABI (tensor creation / H2D copies before a solve, reads after it)
+    PORO_CUDA(cudaStreamCreate(&c.stream));
     PORO_CUDA(cudaMallocHost(&c.h_pin, 8192 * sizeof(double)));
     PORO_CUDA(cudaMalloc(&c.d_scal, ((size_t)Ctx::kScal + 8192) * sizeof(double)));
     PORO_CUDA(cudaMemset(c.d_scal, 0, ((size_t)Ctx::kScal + 8192) * sizeof(double)));
@@ -366,6 +369,8 @@ static void permute_matrix(poro_ctx* h, const Csr& raw, Csr& out) {
 static std::unique_ptr<KSP> make_inner(poro_ctx* h, MatOp* op, const std::string& ksp_type, const std::string& pc_type,
                                        const std::string& prefix, int bs, const double* coords, int cdim) {
     Ctx& c = h->c;
+    if (c.has_opt("-poro_verbose"))
+        fprintf(stderr, "  [pc] inner solver %s: n=%d nnz=%lld bs=%d\n", prefix.c_str(), op->mat().nrows, (long long)op->mat().nnz, bs);
     auto k = std::make_unique<KSP>();
     k->ctx = &c;
     k->A = op;
@@ -605,6 +610,18 @@ int poro_pc_block_info(poro_pc* pc, const char* name, int64_t* nrows, int64_t* n
     API_END
 }
 
+int poro_pc_block_copy(poro_pc* pc, const char* name, int64_t* rowptr, int32_t* col, double* val) {
+    API_BEGIN
+    MatOp* m = find_block(pc, name);
+    if (!m) throw Error(std::string("no such block: ") + name);
+    std::vector<int> rp, ci;
+    std::vector<double> v;
+    csr_to_host(m->mat(), rp, ci, v);
+    for (size_t i = 0; i < rp.size(); ++i) rowptr[i] = rp[i];
+    for (size_t i = 0; i < ci.size(); ++i) { col[i] = ci[i]; val[i] = v[i]; }
+    API_END
+}
+
 static KSP* find_ksp(poro_pc* pc, const std::string& nm) {
     PCBlockCC& cc = pc->cc;
     if (nm == "s") return cc.ksp_s.get();
@@ -717,6 +734,20 @@ int poro_ksp_residual_history(poro_ksp* k, double* out, int cap, int* n) {
     int m = (int)k->ksp.history.size();
     if (n) *n = m;
     for (int i = 0; i < m && i < cap; ++i) out[i] = k->ksp.history[i];
+    API_END
+}
+
+int poro_ksp_profile(poro_ksp* k, int enable, double* op_ms, int64_t* op_calls, int64_t* op_bytes) {
+    API_BEGIN
+    KSP& s = k->ksp;
+    s.profile_flush();
+    if (op_ms) *op_ms = s.op_ms;
+    if (op_calls) *op_calls = s.op_calls;
+    if (op_bytes) {
+        const Csr& A = k->A->mat();
+        *op_bytes = 12 * A.nnz + 4 * ((int64_t)A.nrows + 1) + 8 * (int64_t)A.nrows + 8 * (int64_t)A.ncols;
+    }
+    if (enable >= 0) { s.profile_op = enable != 0; if (enable) { s.op_ms = 0.0; s.op_calls = 0; } }
     API_END
 }
 

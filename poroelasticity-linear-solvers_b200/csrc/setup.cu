@@ -180,18 +180,22 @@ void csr_spgemm(Ctx& c, const Csr& A, const Csr& B, Csr& C) {
             uint64_t* kk = keys.p; double* vv = vals.p;
             int64_t base = hoff[r0];
             int rr0 = r0;
-            // one thread per row of the chunk (rows are short; expansion order = (k, j) order -> deterministic)
-            pfor(c, (int64_t)(r1 - r0), [=] __device__(int64_t t) {
-                int i = rr0 + (int)t;
+            // one warp per row of the chunk; lanes stride over the row of B selected by each a_ik.  The
+            // position of every product is a pure function of (i, k, q), so the emission is deterministic.
+            int nrows_chunk = r1 - r0;
+            pfor(c, (int64_t)nrows_chunk * 32, [=] __device__(int64_t gt) {
+                int t = (int)(gt >> 5), lane = (int)(gt & 31);
+                int i = rr0 + t;
                 int64_t pos = of[i] - base;
                 for (int k = arp[i]; k < arp[i + 1]; ++k) {
                     int j = ac[k];
                     double a = av[k];
-                    for (int q = brp[j]; q < brp[j + 1]; ++q) {
-                        kk[pos] = ((uint64_t)(uint32_t)t << 32) | (uint32_t)bc[q];
-                        vv[pos] = a * bv[q];
-                        ++pos;
+                    int b0 = brp[j], b1 = brp[j + 1];
+                    for (int q = b0 + lane; q < b1; q += 32) {
+                        kk[pos + (q - b0)] = ((uint64_t)(uint32_t)t << 32) | (uint32_t)bc[q];
+                        vv[pos + (q - b0)] = a * bv[q];
                     }
+                    pos += b1 - b0;
                 }
             });
         }

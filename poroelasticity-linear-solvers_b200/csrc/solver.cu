@@ -144,6 +144,33 @@ int KSP::converged(double rn, int it, double& rnorm0, double& ttol) const {
     return 0;
 }
 
+KSP::~KSP() {
+    for (auto e : ev) cudaEventDestroy(e);
+}
+
+void KSP::op_apply(const double* x, double* y, SpmvMode mode, const double* z) {
+    if (!profile_op) { A->apply(x, y, mode, z); return; }
+    if (ev_used + 2 > ev.size()) {
+        for (int i = 0; i < 2; ++i) { cudaEvent_t e; PORO_CUDA(cudaEventCreate(&e)); ev.push_back(e); }
+    }
+    PORO_CUDA(cudaEventRecord(ev[ev_used], ctx->stream));
+    A->apply(x, y, mode, z);
+    PORO_CUDA(cudaEventRecord(ev[ev_used + 1], ctx->stream));
+    ev_used += 2;
+}
+
+void KSP::profile_flush() {
+    if (!ev_used) return;
+    PORO_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i + 1 < ev_used; i += 2) {
+        float ms = 0.f;
+        PORO_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+        op_ms += ms;
+        op_calls++;
+    }
+    ev_used = 0;
+}
+
 void KSP::solve(const double* b, double* x) {
     calls++;
     history.clear();
@@ -161,6 +188,7 @@ void KSP::solve(const double* b, double* x) {
     else if (type == "fgmres") solve_gmres(b, x, true);
     else throw Error("unsupported ksp type '" + type + "' (prefix " + prefix + ")");
     total_its += its;
+    if (profile_op) profile_flush();
 }
 
 void KSP::solve_gmres(const double* b, double* x, bool flexible) {
@@ -201,9 +229,9 @@ void KSP::solve_gmres(const double* b, double* x, bool flexible) {
         while (reason == 0 && j < m && its < max_it) {
             double* vj = V.p + (size_t)j * n;
             double* w = V.p + (size_t)(j + 1) * n;
-            if (flexible) { double* zj = Z.p + (size_t)j * n; pc->apply(vj, zj); A->apply(zj, w); }
-            else if (rpc) { pc->apply(vj, w1.p); A->apply(w1.p, w); }
-            else { A->apply(vj, w1.p); pc->apply(w1.p, w); }
+            if (flexible) { double* zj = Z.p + (size_t)j * n; pc->apply(vj, zj); op_apply(zj, w); }
+            else if (rpc) { pc->apply(vj, w1.p); op_apply(w1.p, w); }
+            else { op_apply(vj, w1.p); pc->apply(w1.p, w); }
             // classical Gram-Schmidt: one multi-dot pass, one multi-axpy(+norm) pass
             vec_mdot(c, V.p, n, j + 1, w, n, d_h, false);
             allreduce_sum(c, d_h, j + 1);

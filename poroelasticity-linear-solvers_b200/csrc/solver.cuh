@@ -96,6 +96,15 @@ struct KSP {
     // work
     DBuf<double> V, Z, w1, w2, w3;
     int v_cols = 0;
+    // optional live profile of the operator product (CUDA events on the launching stream)
+    bool profile_op = false;
+    std::vector<cudaEvent_t> ev;
+    size_t ev_used = 0;
+    double op_ms = 0.0;
+    int64_t op_calls = 0;
+    void op_apply(const double* x, double* y, SpmvMode mode = SPMV_SET, const double* z = nullptr);
+    void profile_flush();
+    ~KSP();
 
     void set_from_options(const std::string& prefix);
     void solve(const double* b, double* x);     // zero initial guess

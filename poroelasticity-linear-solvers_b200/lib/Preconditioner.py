@@ -73,6 +73,14 @@ class PreconditionerCC(object):
         _capi.check(self.ctx.lib.poro_pc_block_info(self.h, name.encode(), C.byref(r), C.byref(c), C.byref(z)))
         return r.value, c.value, z.value
 
+    def block(self, name):
+        """Copy of a device block as scipy CSR (blocks: ss sf sp ff fp pp fps fpfp schur diff)."""
+        import scipy.sparse as sp
+        r, c, z = self.block_info(name)
+        rp, ci, v = np.zeros(r + 1, np.int64), np.zeros(z, np.int32), np.zeros(z, np.float64)
+        _capi.check(self.ctx.lib.poro_pc_block_copy(self.h, name.encode(), _capi._ptr(rp), _capi._ptr(ci), _capi._ptr(v)))
+        return sp.csr_matrix((v, ci, rp), shape=(r, c))
+
     def amg_info(self, name):
         rows, nnz, nl = (C.c_int64 * 32)(), (C.c_int64 * 32)(), C.c_int()
         _capi.check(self.ctx.lib.poro_pc_amg_info(self.h, name.encode(), rows, nnz, 32, C.byref(nl)))

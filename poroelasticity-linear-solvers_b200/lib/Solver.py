@@ -45,6 +45,12 @@ class _KSP:
     def mult(self, x, y):
         _capi.check(self.ctx.lib.poro_ksp_mult(self.h, _capi._ptr(_tensor(x)), _capi._ptr(_tensor(y))))
 
+    def profile(self, enable=-1):
+        """(ms, calls, algorithmic bytes per product) of the outer SpMV measured by CUDA events."""
+        ms, calls, nbytes = C.c_double(), C.c_int64(), C.c_int64()
+        _capi.check(self.ctx.lib.poro_ksp_profile(self.h, int(enable), C.byref(ms), C.byref(calls), C.byref(nbytes)))
+        return ms.value, calls.value, nbytes.value
+
     def getIterationNumber(self):
         return self.its
 
