@@ -1,0 +1,124 @@
+"""CPU: the Krylov / block-PC / AAR restatements against direct solves and each other."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from oracle.aar import AAR, AndersonAcceleration, gram_solve
+from oracle.blockpc import BlockPC, exact_solvers
+from oracle.krylov import cg, gmres
+from oracle.problems import swelling
+
+
+def _lap(n):
+    return sp.diags([-1, 2.5, -1], [-1, 0, 1], shape=(n, n)).tocsr()
+
+
+def test_gmres_left_right_flexible_match_direct():
+    A = _lap(60) + sp.diags(np.linspace(0, 1, 59), 1)
+    b = np.sin(np.arange(60.0))
+    xd = spla.spsolve(A.tocsc(), b)
+    M = lambda v: v / A.diagonal()
+    for kw in (dict(pc_side="left"), dict(pc_side="right"), dict(flexible=True), dict(pc_side="right", cgs2=True)):
+        r = gmres(lambda v: A @ v, b, M, rtol=1e-12, atol=0, max_it=200, restart=200, **kw)
+        assert r.reason == 2
+        assert np.linalg.norm(r.x - xd) <= 1e-9 * np.linalg.norm(xd)
+    # restart shorter than the iteration count still converges, with more iterations
+    r1 = gmres(lambda v: A @ v, b, M, rtol=1e-10, atol=0, max_it=500, restart=5, pc_side="right")
+    r2 = gmres(lambda v: A @ v, b, M, rtol=1e-10, atol=0, max_it=500, restart=500, pc_side="right")
+    assert r1.reason == 2 and r1.its >= r2.its
+    # right preconditioning monitors the true residual
+    assert abs(r2.history[-1] - np.linalg.norm(b - A @ r2.x)) <= 1e-8 * np.linalg.norm(b)
+
+
+def test_gmres_maxit_and_reasons():
+    A = _lap(80)
+    b = np.ones(80)
+    r = gmres(lambda v: A @ v, b, None, rtol=1e-14, atol=0, max_it=3, restart=3)
+    assert r.reason == -3 and r.its == 3
+    r = gmres(lambda v: A @ v, np.zeros(80), None)
+    assert r.its == 0 and r.reason in (2, 3)
+
+
+@pytest.mark.parametrize("norm_type", ["preconditioned", "unpreconditioned", "natural"])
+def test_cg_matches_direct(norm_type):
+    A = _lap(100)
+    b = np.cos(np.arange(100.0))
+    r = cg(lambda v: A @ v, b, lambda v: v / 2.5, rtol=1e-12, atol=0, max_it=500, norm_type=norm_type)
+    assert r.reason == 2
+    assert np.linalg.norm(r.x - spla.spsolve(A.tocsc(), b)) <= 1e-9 * np.linalg.norm(b)
+
+
+def test_cg_flags_indefinite():
+    A = sp.diags([1.0, -1.0, 2.0]).tocsr()
+    r = cg(lambda v: A @ v, np.ones(3), None, rtol=1e-12, max_it=10)
+    assert r.reason == -8
+
+
+# iteration counts of the exact-block configuration (petsc-options-exact semantics) recorded from this
+# oracle; they pin the restatement against accidental change (NOT reference outputs: parity unpinned)
+PINNED = {(2, 10, "diagonal"): 8, (2, 10, "diagonal 3-way"): 15, (2, 10, "undrained"): 52, (3, 3, "diagonal"): 7}
+
+
+@pytest.mark.parametrize("key", list(PINNED))
+def test_exact_block_gmres_counts(key):
+    dim, N, pct = key
+    s, par = swelling(dim, N, pct)
+    pc = BlockPC(s, exact_solvers())
+    r = gmres(lambda v: s.A @ v, s.b, pc, rtol=par["solver rtol"], atol=par["solver atol"], dtol=1e20,
+              max_it=par["solver maxiter"], restart=par["solver maxiter"], pc_side="right")
+    assert r.its == PINNED[key]
+    xd = spla.spsolve(s.A.tocsc(), s.b)
+    assert np.linalg.norm(s.b - s.A @ r.x) <= max(par["solver rtol"] * np.linalg.norm(s.b), par["solver atol"]) * 1.01
+    # the system is badly scaled across fields (entries from 1e-10 to 1e4): a 1e-6 residual only bounds the
+    # error loosely, which is why the GPU parity tests tighten rtol before comparing solutions
+    assert np.linalg.norm(r.x - xd) / np.linalg.norm(xd) < 5e-2
+
+
+def test_block_pc_is_exact_inverse_of_block_triangular_P():
+    s, _ = swelling(2, 4, "diagonal")
+    pc = BlockPC(s, exact_solvers())
+    x = np.random.default_rng(0).standard_normal(s.n)
+    # 2-way: M = [[P_ss, 0], [P_fp,s, P_fp,fp]] (the s<-fp couplings of P are dropped, Preconditioner.py:219-246)
+    y = pc(x)
+    My = np.zeros_like(x)
+    My[s.is_s] = pc.Ms_s @ y[s.is_s]
+    My[s.is_fp] = pc.Mfp_s @ y[s.is_s] + pc.Mfp_fp @ y[s.is_fp]
+    assert np.linalg.norm(My - x) <= 1e-9 * np.linalg.norm(x)
+
+
+def test_aar_converges_and_quirks():
+    s, par = swelling(2, 6, "diagonal")
+    A = lambda v: s.A @ v
+    a = AAR(10, 5, 1, 1, A, BlockPC(s, exact_solvers()), atol=1e-8, rtol=1e-6, maxiter=500)
+    x = a.solve(s.b)
+    xd = spla.spsolve(s.A.tocsc(), s.b)
+    assert a.it < 100 and np.linalg.norm(x - xd) <= 1e-6 * np.linalg.norm(xd)
+    # Richardson everywhere except every p-th iteration (lib/AAR.py:94)
+    assert a.types[0] == "R" and a.types[4] == "A" and a.types[3] == "R"
+    # error0 is the UNpreconditioned initial residual (lib/AAR.py:67)
+    assert abs(a.history[0] - np.linalg.norm(s.b)) < 1e-14
+    # Gram-based least squares (the GPU formulation) gives the same iterates up to conditioning
+    g = AAR(10, 5, 1, 1, A, BlockPC(s, exact_solvers()), atol=1e-8, rtol=1e-6, maxiter=500, lstsq="gram")
+    xg = g.solve(s.b)
+    assert abs(g.it - a.it) <= 2 and np.linalg.norm(xg - xd) <= 1e-6 * np.linalg.norm(xd)
+
+
+def test_gram_solve_rank_deficient():
+    rng = np.random.default_rng(0)
+    F = rng.standard_normal((50, 3))
+    F = np.concatenate([F, F[:, :1]], axis=1)        # duplicate column -> singular Gram matrix
+    f = rng.standard_normal(50)
+    a = gram_solve(F.T @ F, -(F.T @ f))
+    ref = np.linalg.lstsq(F, -f, rcond=None)[0]
+    assert np.linalg.norm(F @ a - F @ ref) <= 1e-9 * np.linalg.norm(f)
+
+
+def test_anderson_acceleration_fixed_point():
+    # x <- g(x) = 0.5 x + c has fixed point 2c; Anderson(1) on the outputs reaches it immediately
+    c = np.array([1.0, -2.0, 3.0])
+    acc = AndersonAcceleration(2)
+    x = np.zeros(3)
+    for _ in range(6):
+        x = acc.get_next_vector(0.5 * x + c)
+    assert np.linalg.norm(x - 2 * c) < 1e-10
