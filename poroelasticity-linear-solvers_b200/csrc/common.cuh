@@ -127,7 +127,10 @@ struct Csr {
     DBuf<int> rowptr;      // nrows+1 (nnz < 2^31 per local matrix, checked at creation)
     DBuf<int> col;
     DBuf<double> val;
-    int lanes = 0;         // lanes per row chosen for SpMV
+    int lanes = 0;         // lanes per row of the fallback vector-CSR SpMV
+    // row blocks of the CSR-stream SpMV, built lazily at the first product (-1 = not built, 0 = unusable)
+    mutable int nblk = -1;
+    mutable DBuf<int> blk_row;
     double avg_row() const { return nrows ? (double)nnz / nrows : 0.0; }
 };
 

@@ -5,17 +5,23 @@
 // Ms_f.mult / Ms_p.mult of the block sweeps (lib/Preconditioner.py:180,184,192-193,232).
 // The reference's "mult then aypx(-1)" pairs are fused: y = z - A x in one pass.
 //
-// Kernel: "vector CSR" -- a group of L lanes (L = 2..32, chosen from the mean row length)
-// walks one row; lane l reads val/col at start+l, start+l+L, ... so every warp-wide load of
-// the matrix streams is a contiguous, fully coalesced segment; the matrix streams use
-// streaming (evict-first) loads so that L1/L2 keep the gathered x entries; partial sums
-// are combined by warp shuffles.  HBM-bound: algorithmic bytes = 12 nnz + 4 (nrows+1) +
-// 8 nrows + 8 ncols.
+// Primary kernel: "CSR stream".  The rows are packed (once, lazily) into row blocks of at most
+// kCap nonzeros.  A CTA of 256 threads streams its block's val/col with perfectly coalesced,
+// evict-first loads -- kNt independent loads of each per thread in flight before the first
+// dependent gather of x -- writes the products val*x[col] to shared memory, and then sub-warps
+// of G lanes reduce each row from shared memory (shuffle tree) and apply the epilogue.  No
+// lane is idle on short rows and no row length leaves a warp partially filled in the
+// streaming phase, which is what bounds the plain vector-CSR kernel (kept below as the
+// fallback for matrices with a row longer than kCap).
+// HBM-bound: algorithmic bytes = 12 nnz + 4 (nrows+1) + 8 nrows + 8 ncols.
 #include "common.cuh"
+#include <algorithm>
 
 namespace poro {
 
 static constexpr int kSpmvBlock = 256;
+static constexpr int kNt = 8;                       // nonzeros per thread in the streaming phase
+static constexpr int kCap = kSpmvBlock * kNt;       // nonzeros per row block (16 KB of products)
 
 struct Epilogue {
     int mode;                 // SpmvMode, or 3 = Chebyshev step, 4 = dot
@@ -24,25 +30,104 @@ struct Epilogue {
     const double* d_old; double* d_new; double* r; double* xv; const double* dinv; double c1, c2;
 };
 
-template <int L>
-__device__ __forceinline__ double group_sum(double v) {
-#pragma unroll
-    for (int o = L / 2; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o, L);
-    return v;
+template <int MODE>
+__device__ __forceinline__ double apply_epilogue(const Epilogue& ep, int row, double sum, const double* __restrict__ x,
+                                                 double* __restrict__ y) {
+    if (MODE == SPMV_SET) y[row] = sum;
+    else if (MODE == SPMV_SUB) y[row] = ep.z[row] - sum;
+    else if (MODE == SPMV_ADD) y[row] = ep.z[row] + sum;
+    else if (MODE == 3) {
+        const double rn = ep.r[row] - sum;
+        const double dn = ep.c1 * ep.d_old[row] + ep.c2 * ep.dinv[row] * rn;
+        ep.r[row] = rn;
+        ep.d_new[row] = dn;
+        ep.xv[row] += dn;
+    } else if (MODE == 4) {
+        y[row] = sum;
+        return sum * x[row];
+    }
+    return 0.0;
 }
 
+__device__ __forceinline__ double block_sum_256(double v, double* sm) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 0; w < kSpmvBlock / 32; ++w) t += sm[w];
+    }
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CSR stream
+// ---------------------------------------------------------------------------------------------
+template <int G, int MODE>
+__global__ void __launch_bounds__(kSpmvBlock) k_spmv_stream(const int* __restrict__ blk_row, const int* __restrict__ rowptr,
+                                                            const int* __restrict__ col, const double* __restrict__ val,
+                                                            const double* __restrict__ x, double* __restrict__ y, Epilogue ep,
+                                                            double* __restrict__ dot_partial) {
+    __shared__ double prod[kCap];
+    __shared__ double red[kSpmvBlock / 32];
+    const int r0 = blk_row[blockIdx.x], r1 = blk_row[blockIdx.x + 1];
+    const int p0 = rowptr[r0];
+    const int cnt = rowptr[r1] - p0;
+    const int* __restrict__ cb = col + p0;
+    const double* __restrict__ vb = val + p0;
+    // phase 1: stream the block's nonzeros; all matrix loads are issued before the first gather
+    int cidx[kNt];
+    double v[kNt];
+#pragma unroll
+    for (int t = 0; t < kNt; ++t) {
+        const int i = threadIdx.x + t * kSpmvBlock;
+        cidx[t] = i < cnt ? __ldcs(cb + i) : -1;
+        v[t] = i < cnt ? __ldcs(vb + i) : 0.0;
+    }
+    double xv[kNt];
+#pragma unroll
+    for (int t = 0; t < kNt; ++t) xv[t] = cidx[t] >= 0 ? __ldg(x + cidx[t]) : 0.0;
+#pragma unroll
+    for (int t = 0; t < kNt; ++t) {
+        const int i = threadIdx.x + t * kSpmvBlock;
+        if (i < cnt) prod[i] = v[t] * xv[t];
+    }
+    __syncthreads();
+    // phase 2: G lanes per row reduce from shared memory
+    const int lane = threadIdx.x & (G - 1);
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+    double contrib = 0.0;
+    for (int row = r0 + threadIdx.x / G; row < r1; row += kSpmvBlock / G) {
+        const int a = rowptr[row] - p0, b = rowptr[row + 1] - p0;
+        double s = 0.0;
+        for (int i = a + lane; i < b; i += G) s += prod[i];
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) s += __shfl_down_sync(gmask, s, o, G);
+        if (lane == 0) contrib += apply_epilogue<MODE>(ep, row, s, x, y);
+    }
+    if (MODE == 4) {
+        double t = block_sum_256(contrib, red);
+        if (threadIdx.x == 0) dot_partial[blockIdx.x] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// vector CSR (fallback): L lanes walk one row
+// ---------------------------------------------------------------------------------------------
 template <int L, int MODE>
 __global__ void __launch_bounds__(kSpmvBlock) k_spmv(int nrows, const int* __restrict__ rowptr,
                                                      const int* __restrict__ col, const double* __restrict__ val,
                                                      const double* __restrict__ x, double* __restrict__ y, Epilogue ep,
                                                      double* __restrict__ dot_partial) {
+    __shared__ double red[kSpmvBlock / 32];
     const int lane = threadIdx.x & (L - 1);
     const int row = (int)(((int64_t)blockIdx.x * kSpmvBlock + threadIdx.x) / L);
     double sum = 0.0;
     if (row < nrows) {
         const int start = rowptr[row], end = rowptr[row + 1];
         int k = start + lane;
-        // two independent streams per lane for memory-level parallelism
         double s0 = 0.0, s1 = 0.0;
         for (; k + L < end; k += 2 * L) {
             const int c0 = __ldcs(col + k), c1 = __ldcs(col + k + L);
@@ -53,69 +138,92 @@ __global__ void __launch_bounds__(kSpmvBlock) k_spmv(int nrows, const int* __res
         if (k < end) s0 = fma(__ldcs(val + k), __ldg(x + __ldcs(col + k)), s0);
         sum = s0 + s1;
     }
-    sum = group_sum<L>(sum);
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o, L);
     double contrib = 0.0;
-    if (row < nrows && lane == 0) {
-        if (MODE == SPMV_SET) y[row] = sum;
-        else if (MODE == SPMV_SUB) y[row] = ep.z[row] - sum;
-        else if (MODE == SPMV_ADD) y[row] = ep.z[row] + sum;
-        else if (MODE == 3) {
-            const double rn = ep.r[row] - sum;
-            const double dn = ep.c1 * ep.d_old[row] + ep.c2 * ep.dinv[row] * rn;
-            ep.r[row] = rn;
-            ep.d_new[row] = dn;
-            ep.xv[row] += dn;
-        } else if (MODE == 4) {
-            y[row] = sum;
-            contrib = sum * x[row];
-        }
-    }
+    if (row < nrows && lane == 0) contrib = apply_epilogue<MODE>(ep, row, sum, x, y);
     if (MODE == 4) {
-        // block-level reduction of p.w, one partial per block (summed later in a fixed order)
-        __shared__ double sm[kSpmvBlock / 32];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_down_sync(0xffffffffu, contrib, o);
-        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = contrib;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double t = 0.0;
-#pragma unroll
-            for (int w = 0; w < kSpmvBlock / 32; ++w) t += sm[w];
-            dot_partial[blockIdx.x] = t;
-        }
+        double t = block_sum_256(contrib, red);
+        if (threadIdx.x == 0) dot_partial[blockIdx.x] = t;
     }
 }
 
 void csr_choose_lanes(Csr& A) {
     double a = A.avg_row();
     A.lanes = a <= 3 ? 2 : a <= 6 ? 4 : a <= 12 ? 8 : a <= 24 ? 16 : 32;
+    A.nblk = -1;     // row blocks are (re)built lazily at the first product
+}
+
+// packs whole rows into blocks of at most kCap nonzeros (host side, once per matrix)
+static void build_row_blocks(Ctx& c, const Csr& A) {
+    std::vector<int> rp((size_t)A.nrows + 1);
+    PORO_CUDA(cudaMemcpyAsync(rp.data(), A.rowptr.p, rp.size() * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    PORO_CUDA(cudaStreamSynchronize(c.stream));
+    std::vector<int> blk;
+    blk.reserve((size_t)(A.nnz / kCap) * 2 + 16);
+    int r = 0;
+    bool ok = true;
+    while (r < A.nrows) {
+        blk.push_back(r);
+        int start = r;
+        const int limit = rp[r] + kCap;
+        // largest r with rp[r] <= limit, but at most 8192 rows per block (keeps phase 2 short for empty rows)
+        int hi = (int)(std::upper_bound(rp.begin() + r + 1, rp.end(), limit) - rp.begin()) - 1;
+        hi = std::min(hi, start + 8192);
+        if (hi <= start) { ok = false; break; }      // a single row exceeds the block capacity
+        r = hi;
+    }
+    blk.push_back(A.nrows);
+    if (!ok || A.nrows == 0) { A.nblk = 0; return; }
+    A.nblk = (int)blk.size() - 1;
+    A.blk_row.alloc(blk.size());
+    PORO_CUDA(cudaMemcpyAsync(A.blk_row.p, blk.data(), blk.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+    PORO_CUDA(cudaStreamSynchronize(c.stream));
 }
 
 template <int MODE>
-static void launch_spmv(Ctx& c, const Csr& A, const double* x, double* y, const Epilogue& ep, double* dot_partial, int* grid_out) {
-    if (A.nrows == 0) { if (grid_out) *grid_out = 0; return; }
-    int L = A.lanes ? A.lanes : 32;
-    int grid = ceil_div((int64_t)A.nrows * L, kSpmvBlock);
-    if (grid_out) *grid_out = grid;
-#define GO(LL) k_spmv<LL, MODE><<<grid, kSpmvBlock, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, y, ep, dot_partial)
-    switch (L) {
-        case 2: GO(2); break;
-        case 4: GO(4); break;
-        case 8: GO(8); break;
-        case 16: GO(16); break;
-        default: GO(32); break;
-    }
+static int launch_spmv(Ctx& c, const Csr& A, const double* x, double* y, const Epilogue& ep, double* dot_partial) {
+    if (A.nrows == 0) return 0;
+    if (A.nblk < 0) build_row_blocks(c, A);
+    int grid;
+    if (A.nblk > 0) {
+        grid = A.nblk;
+        const double a = A.avg_row();
+        const int G = a <= 1.5 ? 1 : a <= 4 ? 2 : a <= 12 ? 4 : a <= 48 ? 8 : a <= 160 ? 16 : 32;
+#define GO(GG) k_spmv_stream<GG, MODE><<<grid, kSpmvBlock, 0, c.stream>>>(A.blk_row.p, A.rowptr.p, A.col.p, A.val.p, x, y, ep, dot_partial)
+        switch (G) {
+            case 1: GO(1); break;
+            case 2: GO(2); break;
+            case 4: GO(4); break;
+            case 8: GO(8); break;
+            case 16: GO(16); break;
+            default: GO(32); break;
+        }
 #undef GO
+    } else {
+        const int L = A.lanes ? A.lanes : 32;
+        grid = ceil_div((int64_t)A.nrows * L, kSpmvBlock);
+#define GO(LL) k_spmv<LL, MODE><<<grid, kSpmvBlock, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, y, ep, dot_partial)
+        switch (L) {
+            case 2: GO(2); break;
+            case 4: GO(4); break;
+            case 8: GO(8); break;
+            case 16: GO(16); break;
+            default: GO(32); break;
+        }
+#undef GO
+    }
     PORO_LAUNCH_CHECK(c);
+    return grid;
 }
 
 void spmv(Ctx& c, const Csr& A, const double* x, double* y, SpmvMode mode, const double* z) {
     Epilogue ep{};
     ep.mode = mode;
     ep.z = z;
-    if (mode == SPMV_SET) launch_spmv<SPMV_SET>(c, A, x, y, ep, nullptr, nullptr);
-    else if (mode == SPMV_SUB) launch_spmv<SPMV_SUB>(c, A, x, y, ep, nullptr, nullptr);
-    else launch_spmv<SPMV_ADD>(c, A, x, y, ep, nullptr, nullptr);
+    if (mode == SPMV_SET) launch_spmv<SPMV_SET>(c, A, x, y, ep, nullptr);
+    else if (mode == SPMV_SUB) launch_spmv<SPMV_SUB>(c, A, x, y, ep, nullptr);
+    else launch_spmv<SPMV_ADD>(c, A, x, y, ep, nullptr);
 }
 
 void spmv_cheb_step(Ctx& c, const Csr& A, const double* d_old, double* d_new, double* r, double* x,
@@ -123,7 +231,7 @@ void spmv_cheb_step(Ctx& c, const Csr& A, const double* d_old, double* d_new, do
     Epilogue ep{};
     ep.mode = 3;
     ep.d_old = d_old; ep.d_new = d_new; ep.r = r; ep.xv = x; ep.dinv = dinv; ep.c1 = c1; ep.c2 = c2;
-    launch_spmv<3>(c, A, d_old, nullptr, ep, nullptr, nullptr);
+    launch_spmv<3>(c, A, d_old, nullptr, ep, nullptr);
 }
 
 __global__ void k_sum_to(const double* __restrict__ partial, int n, double* __restrict__ out) {
@@ -142,18 +250,17 @@ __global__ void k_sum_to(const double* __restrict__ partial, int n, double* __re
 }
 
 void spmv_dot(Ctx& c, const Csr& A, const double* p, double* w, double* d_dot) {
-    PORO_REQUIRE(A.nrows == A.ncols || true, "");
     Epilogue ep{};
     ep.mode = 4;
-    int L = A.lanes ? A.lanes : 32;
-    int grid = ceil_div((int64_t)A.nrows * L, kSpmvBlock);
+    if (A.nblk < 0) build_row_blocks(c, A);
+    const int L = A.lanes ? A.lanes : 32;
+    const int64_t grid = A.nblk > 0 ? A.nblk : ceil_div((int64_t)A.nrows * L, kSpmvBlock);
     if (grid <= Ctx::kScal) {
-        launch_spmv<4>(c, A, p, w, ep, c.d_scal, nullptr);
-        k_sum_to<<<1, 256, 0, c.stream>>>(c.d_scal, grid, d_dot);
+        int g = launch_spmv<4>(c, A, p, w, ep, c.d_scal);
+        k_sum_to<<<1, 256, 0, c.stream>>>(c.d_scal, g, d_dot);
         PORO_LAUNCH_CHECK(c);
     } else {
-        // too many blocks for the partial buffer: plain SpMV + separate dot
-        launch_spmv<SPMV_SET>(c, A, p, w, ep, nullptr, nullptr);
+        launch_spmv<SPMV_SET>(c, A, p, w, ep, nullptr);
         const double* xs[1] = {p};
         const double* ys[1] = {w};
         vec_dots(c, 1, xs, ys, A.nrows, d_dot);
