@@ -6,7 +6,8 @@ throughput, SpMV HBM roofline.
 
 A "step" is ONE complete `Solver.solve(b, x)` of the assembled three-field system from a zero
 initial guess to relative residual 1e-8 (right-preconditioned GMRES + block `diagonal`
-preconditioner with SA-AMG V-cycles, pressure Schur complement) -- set-up (assembly, upload,
+preconditioner: one SA-AMG V-cycle on the solid block, Chebyshev(4) on the mass-dominated fluid block,
+one V-cycle on the selfp pressure Schur complement) -- set-up (assembly, upload,
 AMG hierarchy) is outside the timed region exactly as the reference times only `ksp.solve`
 (lib/Solver.py:148-152).  `value` = DoFs x outer iterations / second over the K timed steps
 (whole job, all ranks); `e2e` is the same through the host-buffer entry point
@@ -39,16 +40,20 @@ BENCH_OPTIONS = """
 -global_ksp_pc_side right
 -s_ksp_type preonly
 -s_pc_type hypre
+-s_pc_amg_theta 0.04
 -fp_ksp_type preonly
 -fp_pc_fieldsplit_type schur
 -fp_pc_fieldsplit_schur_fact_type lower
 -fp_pc_fieldsplit_schur_precondition selfp
 -fp_pc_fieldsplit_order fp
 -fp_fieldsplit_0_ksp_type preonly
--fp_fieldsplit_0_pc_type hypre
+-fp_fieldsplit_0_pc_type chebyshev
 -fp_fieldsplit_1_ksp_type preonly
 -fp_fieldsplit_1_pc_type hypre
 """
+PHASE_NAMES = {0: "outer_A_apply", 1: "pc_apply", 2: "s_solve", 3: "fp_split0(f)", 4: "fp_split1(p)", 5: "gram_schmidt",
+               6: "fp_coupling", **{8 + l: "s_amg_L%d" % l for l in range(8)}, **{16 + l: "f_amg_L%d" % l for l in range(8)},
+               **{24 + l: "p_amg_L%d" % l for l in range(8)}, 32: "A_remainder_csr", 33: "A_ss", 34: "A_sf", 35: "A_fs", 36: "A_ff"}
 RTOL = 1e-8
 METRIC = "3D swelling GMRES throughput to rtol 1e-8 (DoFs x outer iterations per second)"
 UNIT = "DoF*it/s"
@@ -112,10 +117,11 @@ def oracle_solver(sys_, par, max_it):
     from oracle.krylov import gmres
     dim = sys_.dim
     B = rigid_body_modes(sys_.coords_s, dim)
-    amg_v = lambda M: SAAMG(M, dim, B)
+    amg_s = lambda M: SAAMG(M, dim, B, theta=0.04)                              # -s_pc_amg_theta 0.04
+    cheb_f = lambda M: SAAMG(M, dim, B, max_levels=1, cheby_degree=4)           # -fp_fieldsplit_0_pc_type chebyshev
     amg_p = lambda M: SAAMG(M, 1, None)
-    mkfp = lambda M: SchurLower(M, sys_.nf, sys_.np_, krylov_solver("preonly", amg_v), krylov_solver("preonly", amg_p), "f")
-    pc = BlockPC(sys_, {"s": krylov_solver("preonly", amg_v), "fp": mkfp})
+    mkfp = lambda M: SchurLower(M, sys_.nf, sys_.np_, krylov_solver("preonly", cheb_f), krylov_solver("preonly", amg_p), "f")
+    pc = BlockPC(sys_, {"s": krylov_solver("preonly", amg_s), "fp": mkfp})
     A = sys_.A
 
     def run():
@@ -271,10 +277,12 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     ksp.profile(1)
+    ctx.profile(1)
     l0 = ctx.launch_count()
     dt, its = timed(step_dev, args.steps)
     launches = ctx.launch_count() - l0
     op_ms, op_calls, op_bytes = ksp.profile(0)
+    phases = ctx.profile(0)
     clocks = sampler.stop()
     reason, rnorm = ksp.reason, ksp.rnorm
     for _ in range(1):
@@ -308,6 +316,7 @@ def main():
         "e2e": {"value": n_global * its_e / dt_e, "unit": UNIT, "h2d_bytes_per_step": int(b_host.numel() * 8),
                 "d2h_bytes_per_step": int(x_host.numel() * 8), "ms_per_step": 1e3 * dt_e / args.steps},
         "gpu_launches": int(launches),
+        "phases_ms_per_solve": {PHASE_NAMES.get(k, str(k)): round(v[0] / args.steps, 3) for k, v in sorted(phases.items())},
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_spmv<32,SET> (outer operator y = A x)", "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,

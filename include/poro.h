@@ -132,6 +132,10 @@ int poro_pc_amg_info(poro_pc* pc, const char* name, int64_t* rows, int64_t* nnz,
  * 0 stops, -1 only reads.  op_bytes = algorithmic bytes of one product
  * (12 nnz + 4 (nrows+1) + 8 nrows + 8 ncols). */
 int poro_ksp_profile(poro_ksp* ksp, int enable, double* op_ms, int64_t* op_calls, int64_t* op_bytes);
+/* phase profile (CUDA events on the launching stream): slots 0 outer operator, 1 preconditioner apply,
+ * 2 solid solve, 3 fp split 0, 4 fp split 1, 5 orthogonalisation, 6 fp coupling product,
+ * 8+l / 16+l / 24+l AMG level l (inclusive) of the s / f / p hierarchies.  enable as in poro_ksp_profile. */
+int poro_profile(poro_ctx* ctx, int enable, double* ms, int64_t* calls, int n);
 /* operator y = A x in the solver's internal (field-major) ordering incl. halo exchange */
 int poro_ksp_mult(poro_ksp* ksp, const double* x_dev, double* y_dev);
 

@@ -171,7 +171,7 @@ class Level:
 class SAAMG:
     def __init__(self, A: sp.csr_matrix, bs: int = 1, B: np.ndarray | None = None, theta: float = 0.08,
                  max_levels: int = 10, coarse_size: int = 400, cheby_degree: int = 2, cheby_ratio: float = 10.0,
-                 power_its: int = 15):
+                 power_its: int = 15, dense_limit: int = 4096):
         A = sp.csr_matrix(A)
         n = A.shape[0]
         if B is None:
@@ -212,7 +212,10 @@ class SAAMG:
             L.agg, L.n_agg = agg, n_agg
             A, B, bs = Ac, Bc, B.shape[1]
         Lc = self.levels[-1]
-        Lc.inv = np.linalg.inv(Lc.A.toarray())
+        # coarsest level: dense inverse when small (amg.cu: poro_amg_dense_limit), else smoothing only
+        self.coarse_direct = Lc.A.shape[0] <= dense_limit
+        if self.coarse_direct:
+            Lc.inv = np.linalg.inv(Lc.A.toarray())
 
     def complexity(self):
         return sum(L.A.nnz for L in self.levels) / self.levels[0].A.nnz
@@ -238,7 +241,10 @@ class SAAMG:
     def _cycle(self, l, b):
         L = self.levels[l]
         if l == len(self.levels) - 1:
-            return L.inv @ b
+            if self.coarse_direct:
+                return L.inv @ b
+            x = self._cheby(L, b, np.zeros_like(b), True)
+            return x if len(self.levels) == 1 else self._cheby(L, b, x, False)
         x = self._cheby(L, b, np.zeros_like(b), True)
         r = b - L.A @ x
         xc = self._cycle(l + 1, L.R @ r)

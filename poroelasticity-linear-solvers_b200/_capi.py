@@ -58,6 +58,7 @@ SIGNATURES = {
     "poro_pc_amg_info": [vp, C.c_char_p, c_i64p, c_i64p, C.c_int, C.POINTER(C.c_int)],
     "poro_ksp_mult": [vp, vp, vp],
     "poro_ksp_profile": [vp, C.c_int, c_f64p, c_i64p, c_i64p],
+    "poro_profile": [vp, C.c_int, c_f64p, c_i64p, C.c_int],
 }
 
 
@@ -139,6 +140,12 @@ class Context:
 
     def clear_options(self):
         check(self.lib.poro_options_clear(self.h))
+
+    def profile(self, enable=-1):
+        """Phase profile {slot: (ms, calls)} from CUDA events (slots: see include/poro.h)."""
+        ms, calls = (C.c_double * 40)(), (C.c_int64 * 40)()
+        check(self.lib.poro_profile(self.h, int(enable), ms, calls, 40))
+        return {i: (ms[i], calls[i]) for i in range(40) if calls[i]}
 
     def launch_count(self) -> int:
         return int(self.lib.poro_launch_count(self.h))

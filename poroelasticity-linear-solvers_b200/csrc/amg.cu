@@ -408,6 +408,13 @@ void Amg::setup(Ctx& c, const Csr& A, int bs, const double* B_dev, int k, const 
             });
         }
         Lp->n_agg = n_agg;
+        {
+            // block structure of the transfer operators and of the coarse operator (k modes per aggregate)
+            const int hint = (bs % 3 == 0 && k % 3 == 0) ? 3 : ((bs % 2 == 0 && k % 2 == 0) ? 2 : 0);
+            Lp->P.block_hint = hint;
+            Lp->R.block_hint = hint;
+            Ac.block_hint = k;
+        }
         Anext = std::move(Ac);
         have_next = true;
         B = std::move(Bc);
@@ -469,10 +476,12 @@ void Amg::cheby(int l, const double* b, double* x, bool zero_guess) {
 
 void Amg::cycle(int l, const double* b, double* x) {
     Ctx& c = *ctx;
+    ProfScope ps(c, prof_base >= 0 && l < 8 ? prof_base + l : -1);
     const Csr& A = op(l);
     const int last = (int)levels.size() - 1;
     if (l == last) {
         if (coarse_direct) dense_gemv(c, coarse_inv.p, A.nrows, b, x);
+        else if (levels.size() == 1) cheby(l, b, x, true);            // `chebyshev` PC: one sweep of the full degree
         else { cheby(l, b, x, true); cheby(l, b, x, false); }
         return;
     }

@@ -29,6 +29,7 @@ struct Amg {
     const Csr* A0 = nullptr;        // finest operator is borrowed
     DBuf<double> coarse_inv;
     bool coarse_direct = false;
+    int prof_base = -1;             // phase-profile slot of level 0 (-1: not profiled)
 
     // B: device n x k row-major near-nullspace (may be null -> one constant per component)
     void setup(Ctx& c, const Csr& A, int bs, const double* B_dev, int k, const AmgParams& p);

@@ -1,0 +1,232 @@
+// bsr.cu -- block-CSR (BS x BS, BS = 2 or 3) SpMV for the node-blocked vector fields.
+//
+// The displacement and fluid-velocity blocks (A_ss, A_ff, P_ss, P_ff) and every level of their
+// AMG hierarchies (prolongators included) consist of dense BS x BS node blocks.  Storing them
+// as BSR cuts the matrix stream from 12 to (8 BS^2 + 4) / BS^2 = 8.44 bytes per nonzero (BS = 3)
+// and -- what the ncu profile of the CSR kernel showed to be the real limiter (L1TEX wavefronts
+// of the x gathers, profiles/r1_spmv_stream_csr.md) -- replaces 9 scattered 8-byte gathers by
+// three loads of one contiguous 24-byte node vector.
+//
+// Layout: values are interleaved in groups of 32 blocks, val[((p / 32) * BS^2 + e) * 32 + p % 32]
+// for entry e of block p, so that "one thread per block" reads every entry fully coalesced.
+// Kernel: a CTA streams up to kCapB blocks of whole block rows (thread per block, kNtb blocks per
+// thread in flight), writes BS partial sums per block to shared memory, then G lanes per block
+// row reduce them and apply the same epilogues as the CSR kernel (y = Ax, z - Ax, z + Ax, fused
+// Chebyshev step, fused p.Ap).
+// Algorithmic bytes: (8 BS^2 + 4) nnzb + 4 (nbrows + 1) + 8 BS nbrows + 8 BS nbcols.
+#include "common.cuh"
+#include "spmv_epilogue.cuh"
+#include <algorithm>
+
+namespace poro {
+
+static constexpr int kBlk = 256;
+static constexpr int kNtb = 2;
+static constexpr int kCapB = kBlk * kNtb;
+static constexpr int kMaxBRows = 256;     // block rows per chunk (row pointers and row sums live in shared memory)
+
+template <int BS, int G, int MODE, bool DIAG>
+__global__ void __launch_bounds__(kBlk) k_bsr_stream(const int* __restrict__ blk_row, const int* __restrict__ rowptr,
+                                                     const int* __restrict__ col, const double* __restrict__ val,
+                                                     const double* __restrict__ x, double* __restrict__ y, Epilogue ep,
+                                                     double* __restrict__ dot_partial) {
+    __shared__ double part[kCapB * BS];
+    __shared__ double rsum[kMaxBRows * BS];
+    __shared__ int rp[kMaxBRows + 1];
+    __shared__ double red[kBlk / 32];
+    const int R0 = blk_row[blockIdx.x], R1 = blk_row[blockIdx.x + 1];
+    const int nbr = R1 - R0;
+    for (int i = threadIdx.x; i <= nbr; i += kBlk) rp[i] = rowptr[R0 + i];
+    __syncthreads();
+    const int p0 = rp[0];
+    const int cnt = rp[nbr] - p0;
+    // phase 1: one thread per block
+    int c[kNtb];
+#pragma unroll
+    for (int t = 0; t < kNtb; ++t) {
+        const int i = threadIdx.x + t * kBlk;
+        c[t] = i < cnt ? __ldcs(col + p0 + i) : -1;
+    }
+    constexpr int NE = DIAG ? BS : BS * BS;     // stored entries per block
+    double v[kNtb][NE];
+#pragma unroll
+    for (int t = 0; t < kNtb; ++t) {
+        const int p = p0 + threadIdx.x + t * kBlk;
+        const double* vb = val + ((size_t)(p >> 5) * NE) * 32 + (p & 31);
+#pragma unroll
+        for (int e = 0; e < NE; ++e) v[t][e] = c[t] >= 0 ? __ldcs(vb + e * 32) : 0.0;
+    }
+#pragma unroll
+    for (int t = 0; t < kNtb; ++t) {
+        const int i = threadIdx.x + t * kBlk;
+        if (c[t] >= 0) {
+            double xv[BS];
+#pragma unroll
+            for (int j = 0; j < BS; ++j) xv[j] = __ldg(x + (size_t)c[t] * BS + j);
+#pragma unroll
+            for (int k = 0; k < BS; ++k) {
+                double s = 0.0;
+                if (DIAG) s = v[t][k] * xv[k];
+                else {
+#pragma unroll
+                    for (int j = 0; j < BS; ++j) s = fma(v[t][DIAG ? 0 : k * BS + j], xv[j], s);
+                }
+                part[i * BS + k] = s;
+            }
+        }
+    }
+    __syncthreads();
+    // phase 2: G lanes per block row reduce the partial sums into rsum
+    const int lane = threadIdx.x & (G - 1);
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+    for (int Rl = threadIdx.x / G; Rl < nbr; Rl += kBlk / G) {
+        const int a = rp[Rl] - p0, b = rp[Rl + 1] - p0;
+        double s[BS];
+#pragma unroll
+        for (int k = 0; k < BS; ++k) s[k] = 0.0;
+        for (int i = a + lane; i < b; i += G) {
+#pragma unroll
+            for (int k = 0; k < BS; ++k) s[k] += part[i * BS + k];
+        }
+#pragma unroll
+        for (int k = 0; k < BS; ++k) {
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) s[k] += __shfl_down_sync(gmask, s[k], o, G);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < BS; ++k) rsum[Rl * BS + k] = s[k];
+        }
+    }
+    __syncthreads();
+    // phase 3: coalesced epilogue over the scalar rows of the chunk
+    double contrib = 0.0;
+    for (int rl = threadIdx.x; rl < nbr * BS; rl += kBlk) contrib += apply_epilogue<MODE>(ep, R0 * BS + rl, rsum[rl], x, y);
+    if (MODE == 4) {
+        double t = block_sum_256(contrib, red);
+        if (threadIdx.x == 0) dot_partial[blockIdx.x] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conversion CSR -> BSR on the device
+// ---------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(256) k_for3(int64_t n, F f) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
+}
+template <class F>
+static void pfor(Ctx& c, int64_t n, F f) {
+    if (n <= 0) return;
+    int64_t g = (n + 255) / 256;
+    int64_t cap = (int64_t)c.sm_count * 16;
+    k_for3<<<(int)(g < cap ? g : cap), 256, 0, c.stream>>>(n, f);
+    PORO_LAUNCH_CHECK(c);
+}
+
+bool bsr_from_csr(Ctx& c, const Csr& A, int BS, Bsr& out, double max_fill) {
+    if (BS < 2 || BS > 3 || A.nrows % BS || A.ncols % BS || A.nnz == 0) return false;
+    const int nbr = A.nrows / BS, nbc = A.ncols / BS;
+    Csr Nb;
+    {
+        DBuf<uint64_t> keys((size_t)A.nnz);
+        DBuf<double> vals((size_t)A.nnz);
+        const int* rp = A.rowptr.p; const int* cc = A.col.p;
+        uint64_t* kk = keys.p; double* vv = vals.p;
+        pfor(c, A.nrows, [=] __device__(int64_t i) {
+            for (int k = rp[i]; k < rp[i + 1]; ++k) {
+                kk[k] = ((uint64_t)(uint32_t)((int)i / BS) << 32) | (uint32_t)(cc[k] / BS);
+                vv[k] = 1.0;
+            }
+        });
+        coo_to_csr(c, nbr, nbc, A.nnz, keys, vals, Nb, COMBINE_SUM);
+    }
+    const int64_t nnzb = Nb.nnz;
+    // blocks with entries only on their diagonal (scalar matrix (x) I, rows possibly zeroed by BCs)?
+    DBuf<int> offd(1);
+    offd.zero(c.stream);
+    {
+        const int* rp = A.rowptr.p; const int* cc = A.col.p; int* od = offd.p;
+        pfor(c, A.nrows, [=] __device__(int64_t i) {
+            int n = 0;
+            for (int k = rp[i]; k < rp[i + 1]; ++k) n += ((int)i % BS) != (cc[k] % BS);
+            if (n) atomicAdd(od, n);
+        });
+    }
+    int h_offd = 0;
+    PORO_CUDA(cudaMemcpyAsync(&h_offd, offd.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    PORO_CUDA(cudaStreamSynchronize(c.stream));
+    const bool diag = h_offd == 0;
+    const int NE = diag ? BS : BS * BS;
+    // byte break-even against CSR (12 B / nonzero): (8 NE + 4) nnzb <= max_fill-scaled budget
+    if ((double)nnzb * (8.0 * NE + 4.0) > max_fill * 8.44 * (double)A.nnz) return false;
+    out.bs = BS; out.nbrows = nbr; out.nbcols = nbc; out.nnzb = nnzb; out.diag_only = diag;
+    out.rowptr = std::move(Nb.rowptr);
+    out.col = std::move(Nb.col);
+    const size_t ngroups = (size_t)((nnzb + 31) / 32);
+    out.val.alloc(ngroups * 32 * NE);
+    out.val.zero(c.stream);
+    {
+        const int* rp = A.rowptr.p; const int* cc = A.col.p; const double* av = A.val.p;
+        const int* brp = out.rowptr.p; const int* bcc = out.col.p;
+        double* bv = out.val.p;
+        pfor(c, A.nrows, [=] __device__(int64_t i) {
+            const int I = (int)i / BS, ri = (int)i % BS;
+            const int b0 = brp[I], b1 = brp[I + 1];
+            for (int k = rp[i]; k < rp[i + 1]; ++k) {
+                const int J = cc[k] / BS, rj = cc[k] % BS;
+                int lo = b0, hi = b1;
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (bcc[mid] < J) lo = mid + 1; else hi = mid; }
+                const size_t p = (size_t)lo;
+                bv[((p >> 5) * NE + (size_t)(diag ? ri : ri * BS + rj)) * 32 + (p & 31)] = av[k];
+            }
+        });
+    }
+    // pack whole block rows into chunks of at most kCapB blocks
+    std::vector<int> rp((size_t)nbr + 1);
+    PORO_CUDA(cudaMemcpyAsync(rp.data(), out.rowptr.p, rp.size() * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    PORO_CUDA(cudaStreamSynchronize(c.stream));
+    std::vector<int> blk;
+    int r = 0;
+    while (r < nbr) {
+        blk.push_back(r);
+        const int limit = rp[r] + kCapB;
+        int hi = (int)(std::upper_bound(rp.begin() + r + 1, rp.end(), limit) - rp.begin()) - 1;
+        hi = std::min(hi, r + kMaxBRows);
+        if (hi <= r) return false;                 // one block row longer than a chunk
+        r = hi;
+    }
+    blk.push_back(nbr);
+    out.nblk = (int)blk.size() - 1;
+    out.blk_row.alloc(blk.size());
+    PORO_CUDA(cudaMemcpyAsync(out.blk_row.p, blk.data(), blk.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+    PORO_CUDA(cudaStreamSynchronize(c.stream));
+    return true;
+}
+
+template <int MODE>
+int bsr_launch(Ctx& c, const Bsr& B, const double* x, double* y, const Epilogue& ep, double* dot_partial) {
+    const double a = B.nbrows ? (double)B.nnzb / B.nbrows : 0.0;
+    const int G = a <= 1.5 ? 1 : a <= 4 ? 2 : a <= 12 ? 4 : a <= 48 ? 8 : a <= 160 ? 16 : 32;
+#define GO(BSS, GG)                                                                                                          \
+    do {                                                                                                                     \
+        if (B.diag_only) k_bsr_stream<BSS, GG, MODE, true><<<B.nblk, kBlk, 0, c.stream>>>(B.blk_row.p, B.rowptr.p, B.col.p, B.val.p, x, y, ep, dot_partial); \
+        else k_bsr_stream<BSS, GG, MODE, false><<<B.nblk, kBlk, 0, c.stream>>>(B.blk_row.p, B.rowptr.p, B.col.p, B.val.p, x, y, ep, dot_partial);          \
+    } while (0)
+#define GOG(BSS) switch (G) { case 1: GO(BSS, 1); break; case 2: GO(BSS, 2); break; case 4: GO(BSS, 4); break; \
+                              case 8: GO(BSS, 8); break; case 16: GO(BSS, 16); break; default: GO(BSS, 32); break; }
+    if (B.bs == 3) { GOG(3) } else { GOG(2) }
+#undef GOG
+#undef GO
+    PORO_LAUNCH_CHECK(c);
+    return B.nblk;
+}
+
+template int bsr_launch<0>(Ctx&, const Bsr&, const double*, double*, const Epilogue&, double*);
+template int bsr_launch<1>(Ctx&, const Bsr&, const double*, double*, const Epilogue&, double*);
+template int bsr_launch<2>(Ctx&, const Bsr&, const double*, double*, const Epilogue&, double*);
+template int bsr_launch<3>(Ctx&, const Bsr&, const double*, double*, const Epilogue&, double*);
+template int bsr_launch<4>(Ctx&, const Bsr&, const double*, double*, const Epilogue&, double*);
+
+}  // namespace poro

@@ -156,6 +156,7 @@ int poro_mat_create_csr(poro_ctx* h, int64_t nrows, int64_t ncols, const int64_t
         PORO_CUDA(cudaMemcpy(A.val.p, val, (size_t)nnz * 8, cudaMemcpyDeviceToDevice));
         csr_choose_lanes(A);
     }
+    m->raw.block_hint = c.opt_i("-poro_mat_block_hint", 0);   // micro-benchmarks: treat the raw matrix as node-blocked
     *out = m.release();
     API_END
 }
@@ -379,7 +380,7 @@ static std::unique_ptr<KSP> make_inner(poro_ctx* h, MatOp* op, const std::string
     std::string pt = c.opt("-" + prefix + "pc_type", pc_type);
     if (pt == "fieldsplit") pt = "amg";
     const Csr* src = &op->mat();
-    if (pt == "hypre" || pt == "amg" || pt == "gamg" || (pt == "lu" && src->nrows > c.opt_i("poro_dense_lu_limit", 8192))) {
+    if (pt == "hypre" || pt == "amg" || pt == "gamg" || pt == "chebyshev" || (pt == "lu" && src->nrows > c.opt_i("poro_dense_lu_limit", 8192))) {
         // the AMG keeps a pointer to its finest operator: it must live as long as the KSP.  A square block
         // (single rank) is used in place; otherwise the owned-column part is cut out and kept in owned_op.
         std::unique_ptr<MatOp> holder;
@@ -407,6 +408,8 @@ static std::unique_ptr<KSP> make_inner(poro_ctx* h, MatOp* op, const std::string
         k->owned_pc = make_pc(c, pt, *src, bs, coords, cdim, prefix);
     }
     k->pc = k->owned_pc.get();
+    if (PCAmg* a = dynamic_cast<PCAmg*>(k->pc))
+        a->amg.prof_base = prefix == "s_" ? 8 : (bs > 1 ? 16 : (prefix.find("fieldsplit") != std::string::npos ? 24 : -1));
     return k;
 }
 
@@ -448,6 +451,7 @@ int poro_pc_setup(poro_ctx* h, poro_mat* A, poro_mat* P, poro_mat* P_diff, const
     const double* cs = fl.coords_s.empty() ? nullptr : fl.coords_s.data();
     const int cdim = fl.coord_dim;
     cc.Ms_s = extract_block(h, *Pp, os, os + ns, {0});
+    if (c.nranks == 1) cc.Ms_s->M.block_hint = bs_v;
     cc.ksp_s = make_inner(h, cc.Ms_s.get(), iksp, ipc, "s_", bs_v, cs, cdim);
     cc.t_s.alloc(ns); cc.t_f.alloc(nf); cc.t_p.alloc(np); cc.t_fp.alloc(nf + np);
     if (cc.three_way) {
@@ -455,6 +459,7 @@ int poro_pc_setup(poro_ctx* h, poro_mat* A, poro_mat* P, poro_mat* P_diff, const
         cc.Ms_f = extract_block(h, *Pp, os, os + ns, {1});
         cc.Ms_p = extract_block(h, *Pp, os, os + ns, {2});
         cc.Mf_f = extract_block(h, *Pp, of, of + nf, {1});
+        if (c.nranks == 1) cc.Mf_f->M.block_hint = bs_v;
         cc.Mf_p = extract_block(h, *Pp, of, of + nf, {2});
         cc.Mp_p = extract_block(h, *Pp, op_, op_ + np, {2});
         {
@@ -500,6 +505,7 @@ int poro_pc_setup(poro_ctx* h, poro_mat* A, poro_mat* P, poro_mat* P_diff, const
             sch->A01 = extract_block(h, *Pp, fl.off[t0], fl.off[t0] + fl.n[t0], {t1});
             sch->A10 = extract_block(h, *Pp, fl.off[t1], fl.off[t1] + fl.n[t1], {t0});
             sch->A11 = extract_block(h, *Pp, fl.off[t1], fl.off[t1] + fl.n[t1], {t1});
+            if (c.nranks == 1) (t0 == 1 ? sch->A00 : sch->A11)->M.block_hint = bs_v;
             // selfp: S = A11 - A10 diag(A00)^-1 A01 on the local (owned) parts
             {
                 Csr a00, a01, a10, a11;
@@ -670,6 +676,31 @@ static std::unique_ptr<MatOp> make_outer_op(poro_ctx* h, poro_mat* A) {
     for (int t = 0; t < 3; ++t)
         if (fl.nh[t]) op->pieces.push_back({&fl.halo[t], fl.off[t], fl.n_owned + fl.hoff[t]});
     if (!op->ref) csr_choose_lanes(op->M);
+    // node-blocked s and f diagonal blocks (owned columns) -> BSR parts; everything else stays in one CSR remainder
+    const int bd = fl.block_dim;
+    if (bd > 1 && fl.n[0] % bd == 0 && fl.n[1] % bd == 0 && c.opt_i("-poro_use_bsr", 1)) {
+        // ss, ff (dense node blocks -> BSR) and sf, fs (mass couplings M (x) I -> diagonal-block BSR)
+        Csr rem;
+        bool have_rem = false;
+        for (int tr = 0; tr < 2; ++tr)
+            for (int tc = 0; tc < 2; ++tc) {
+                const Csr& src = have_rem ? rem : op->mat();
+                auto part = std::make_unique<MatOp::DiagPart>();
+                const int r0 = (int)fl.off[tr], r1 = (int)(fl.off[tr] + fl.n[tr]);
+                const int c0 = (int)fl.off[tc], c1 = (int)(fl.off[tc] + fl.n[tc]);
+                csr_select(c, src, r0, r1, c0, c1, true, part->B);
+                if (part->B.nnz == 0) continue;
+                part->B.block_hint = bd;
+                part->row_off = r0;
+                part->col_off = c0;
+                op->parts.push_back(std::move(part));
+                Csr next;
+                csr_select(c, src, r0, r1, c0, c1, false, next);
+                rem = std::move(next);
+                have_rem = true;
+            }
+        if (have_rem) { op->M = std::move(rem); op->ref = nullptr; }
+    }
     return op;
 }
 
@@ -744,10 +775,32 @@ int poro_ksp_profile(poro_ksp* k, int enable, double* op_ms, int64_t* op_calls, 
     if (op_ms) *op_ms = s.op_ms;
     if (op_calls) *op_calls = s.op_calls;
     if (op_bytes) {
+        // algorithmic bytes of the formats actually launched: CSR remainder + BSR diagonal parts
         const Csr& A = k->A->mat();
-        *op_bytes = 12 * A.nnz + 4 * ((int64_t)A.nrows + 1) + 8 * (int64_t)A.nrows + 8 * (int64_t)A.ncols;
+        int64_t bytes = 12 * A.nnz + 4 * ((int64_t)A.nrows + 1) + 8 * (int64_t)A.nrows + 8 * (int64_t)A.ncols;
+        for (auto& p : k->A->parts) {
+            const Csr& B = p->B;
+            if (B.bsr_state == 1) {
+                const Bsr& b = *B.bsr;
+                const int64_t ne = b.diag_only ? b.bs : b.bs * b.bs;
+                bytes += (8 * ne + 4) * b.nnzb + 4 * ((int64_t)b.nbrows + 1) + 16 * (int64_t)B.nrows + 8 * (int64_t)B.ncols;
+            } else bytes += 12 * B.nnz + 4 * ((int64_t)B.nrows + 1) + 16 * (int64_t)B.nrows + 8 * (int64_t)B.ncols;
+        }
+        *op_bytes = bytes;
     }
     if (enable >= 0) { s.profile_op = enable != 0; if (enable) { s.op_ms = 0.0; s.op_calls = 0; } }
+    API_END
+}
+
+int poro_profile(poro_ctx* h, int enable, double* ms, int64_t* calls, int n) {
+    API_BEGIN
+    Ctx& c = h->c;
+    prof_flush(c);
+    for (int i = 0; i < n && i < Ctx::Prof::kSlots; ++i) { if (ms) ms[i] = c.prof.ms[i]; if (calls) calls[i] = c.prof.calls[i]; }
+    if (enable >= 0) {
+        c.prof.on = enable != 0;
+        if (enable) for (int i = 0; i < Ctx::Prof::kSlots; ++i) { c.prof.ms[i] = 0; c.prof.calls[i] = 0; }
+    }
     API_END
 }
 

@@ -87,6 +87,16 @@ struct Ctx {
     double* d_scal = nullptr;    // device scratch for reductions
     static constexpr int kScal = 1 << 18;   // partials; +8192 doubles of small slots behind it
     int64_t launches = 0;
+    // phase profile: CUDA events on the launching stream, resolved lazily (no sync on the hot path)
+    struct Prof {
+        enum { kSlots = 40 };
+        bool on = false;
+        std::vector<cudaEvent_t> ev;
+        std::vector<int> slot;
+        size_t used = 0;
+        double ms[kSlots] = {0};
+        int64_t calls[kSlots] = {0};
+    } prof;
     // distributed layout
     std::vector<int> neigh;
     int64_t n_owned_raw = -1;
@@ -108,6 +118,32 @@ struct Ctx {
     }
 };
 
+// slots: 0 outer operator, 1 preconditioner apply, 2 solid solve, 3 fp split 0, 4 fp split 1, 5 orthogonalisation,
+//        6 fp coupling product, 8+l / 16+l / 24+l: AMG level l (inclusive) of the s / f / p hierarchy
+struct ProfScope {
+    Ctx& c; int idx = -1;
+    ProfScope(Ctx& c_, int slot) : c(c_) {
+        if (!c.prof.on || slot < 0 || slot >= Ctx::Prof::kSlots) return;
+        auto& p = c.prof;
+        if (p.used + 2 > p.ev.size()) for (int i = 0; i < 64; ++i) { cudaEvent_t e; cudaEventCreate(&e); p.ev.push_back(e); p.slot.push_back(0); }
+        idx = (int)p.used;
+        p.slot[idx] = slot;
+        cudaEventRecord(p.ev[idx], c.stream);
+        p.used += 2;
+    }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord(c.prof.ev[idx + 1], c.stream); }
+};
+inline void prof_flush(Ctx& c) {
+    auto& p = c.prof;
+    if (!p.used) return;
+    cudaStreamSynchronize(c.stream);
+    for (size_t i = 0; i + 1 < p.used; i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.ev[i], p.ev[i + 1]) == cudaSuccess) { p.ms[p.slot[i]] += ms; p.calls[p.slot[i]]++; }
+    }
+    p.used = 0;
+}
+
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // grid for streaming kernels: a few CTAs per SM, never more than needed
@@ -120,6 +156,17 @@ inline int stream_grid(const Ctx& c, int64_t n, int block, int per_thread = 4, i
 
 #define PORO_LAUNCH_CHECK(ctx) do { (ctx).launches++; PORO_CUDA(cudaGetLastError()); } while (0)
 
+// ---- block-CSR companion of a Csr (bsr.cu): BS x BS blocks, values interleaved per 32 blocks ----------
+struct Bsr {
+    int bs = 0, nbrows = 0, nbcols = 0;
+    int64_t nnzb = 0;
+    bool diag_only = false;     // blocks are diagonal (e.g. M (x) I couplings): BS values per block instead of BS^2
+    DBuf<int> rowptr, col;
+    DBuf<double> val;
+    DBuf<int> blk_row;
+    int nblk = 0;
+};
+
 // ---- sparse matrix (device CSR, local rows) ---------------------------------------------------
 struct Csr {
     int nrows = 0, ncols = 0;
@@ -131,6 +178,10 @@ struct Csr {
     // row blocks of the CSR-stream SpMV, built lazily at the first product (-1 = not built, 0 = unusable)
     mutable int nblk = -1;
     mutable DBuf<int> blk_row;
+    // node-block size hint (dofs per mesh node); > 1 makes the first product try a BSR conversion
+    int block_hint = 0;
+    mutable int bsr_state = -1;                 // -1 not tried, 0 rejected (fill-in / shape), 1 in use
+    mutable std::shared_ptr<Bsr> bsr;
     double avg_row() const { return nrows ? (double)nnz / nrows : 0.0; }
 };
 
@@ -181,6 +232,7 @@ void csr_transpose(Ctx& c, const Csr& A, Csr& At);
 void csr_extract(Ctx& c, const Csr& A, const int* row_map, const int* col_map, int new_rows, int new_cols, Csr& C);
 void csr_diag(Ctx& c, const Csr& A, double* d);                          // missing diagonal -> 0
 void csr_copy(Ctx& c, const Csr& A, Csr& B);
+void csr_select(Ctx& c, const Csr& A, int r0, int r1, int c0, int c1, bool inside, Csr& C);
 // C = A + alpha * diag(s) * B  (s may be null)
 void csr_add_scaled(Ctx& c, const Csr& A, const Csr& B, double alpha, const double* s, Csr& C);
 void csr_scale_cols(Ctx& c, Csr& A, const double* s);                    // A = A diag(s)

@@ -283,6 +283,59 @@ void csr_extract(Ctx& c, const Csr& A, const int* row_map, const int* col_map, i
     coo_to_csr(c, new_rows, new_cols, nkeep, keys, vals, C, COMBINE_SUM);
 }
 
+// inside = true : C = A[r0:r1, c0:c1]  (rows and columns renumbered from 0)
+// inside = false: C = A with the entries of the rectangle [r0:r1) x [c0:c1) removed (same shape)
+// Order-preserving (count / scan / fill), no sort needed.
+void csr_select(Ctx& c, const Csr& A, int r0, int r1, int c0, int c1, bool inside, Csr& C) {
+    const int nr = inside ? r1 - r0 : A.nrows;
+    const int rbase = inside ? r0 : 0;
+    DBuf<int64_t> cnt((size_t)nr + 1), off((size_t)nr + 1);
+    {
+        const int* rp = A.rowptr.p; const int* cc = A.col.p;
+        int64_t* cn = cnt.p;
+        pfor(c, (int64_t)nr + 1, [=] __device__(int64_t t) {
+            int64_t s = 0;
+            if (t < nr) {
+                const int i = rbase + (int)t;
+                const bool rin = i >= r0 && i < r1;
+                for (int k = rp[i]; k < rp[i + 1]; ++k) {
+                    const bool in = rin && cc[k] >= c0 && cc[k] < c1;
+                    s += (in == inside) ? 1 : 0;
+                }
+            }
+            cn[t] = s;
+        });
+    }
+    int64_t nnz = scan_exclusive_i64(c, cnt.p, off.p, (int64_t)nr + 1);
+    PORO_REQUIRE(nnz < (int64_t)2147483647, "csr_select: too many nonzeros");
+    C.nrows = nr;
+    C.ncols = inside ? c1 - c0 : A.ncols;
+    C.nnz = nnz;
+    C.rowptr.alloc((size_t)nr + 1);
+    C.col.alloc((size_t)nnz);
+    C.val.alloc((size_t)nnz);
+    {
+        const int* rp = A.rowptr.p; const int* cc = A.col.p; const double* v = A.val.p;
+        const int64_t* of = off.p;
+        int* orp = C.rowptr.p; int* oc = C.col.p; double* ov = C.val.p;
+        const int cshift = inside ? c0 : 0;
+        pfor(c, (int64_t)nr + 1, [=] __device__(int64_t t) {
+            orp[t] = (int)of[t];
+            if (t < nr) {
+                const int i = rbase + (int)t;
+                const bool rin = i >= r0 && i < r1;
+                int64_t p = of[t];
+                for (int k = rp[i]; k < rp[i + 1]; ++k) {
+                    const bool in = rin && cc[k] >= c0 && cc[k] < c1;
+                    if (in == inside) { oc[p] = cc[k] - cshift; ov[p] = v[k]; ++p; }
+                }
+            }
+        });
+    }
+    PORO_CUDA(cudaStreamSynchronize(c.stream));
+    csr_choose_lanes(C);
+}
+
 void csr_diag(Ctx& c, const Csr& A, double* d) {
     const int* rp = A.rowptr.p; const int* cc = A.col.p; const double* v = A.val.p;
     pfor(c, A.nrows, [=] __device__(int64_t i) {

@@ -38,7 +38,14 @@ void MatOp::apply(const double* x, double* y, SpmvMode mode, const double* z) {
         return;
     }
     const double* xe = extended(x);
-    spmv(*ctx, A, xe, y, mode, z);
+    const bool prof = !parts.empty();
+    { ProfScope ps(*ctx, prof ? 32 : -1); spmv(*ctx, A, xe, y, mode, z); }
+    int ip = 0;
+    for (auto& p : parts) {
+        double* yp = y + p->row_off;
+        ProfScope ps(*ctx, 33 + ip++);
+        spmv(*ctx, p->B, xe + p->col_off, yp, mode == SPMV_SET ? SPMV_ADD : mode, yp);
+    }
 }
 
 PCJacobi::PCJacobi(Ctx* c, const Csr& A) : ctx(c) {
@@ -85,7 +92,8 @@ std::unique_ptr<PC> make_pc(Ctx& c, const std::string& pc_type, const Csr& A, in
     if (pc_type == "jacobi") return std::make_unique<PCJacobi>(&c, A);
     bool want_lu = pc_type == "lu" || pc_type == "cholesky";
     if (want_lu && A.nrows <= c.opt_i("poro_dense_lu_limit", 8192)) return std::make_unique<PCDense>(&c, A);
-    if (want_lu || pc_type == "hypre" || pc_type == "amg" || pc_type == "gamg" || pc_type == "ml") {
+    const bool cheb_only = pc_type == "chebyshev";      // Chebyshev(degree) on D^-1 A = a one-level hierarchy
+    if (want_lu || cheb_only || pc_type == "hypre" || pc_type == "amg" || pc_type == "gamg" || pc_type == "ml") {
         auto pc = std::make_unique<PCAmg>();
         AmgParams p;
         p.theta = c.opt_d("-" + prefix + "pc_amg_theta", c.opt_d("-pc_amg_theta", p.theta));
@@ -93,6 +101,11 @@ std::unique_ptr<PC> make_pc(Ctx& c, const std::string& pc_type, const Csr& A, in
         p.coarse_size = c.opt_i("-" + prefix + "pc_amg_coarse_size", c.opt_i("-pc_amg_coarse_size", p.coarse_size));
         p.max_levels = c.opt_i("-" + prefix + "pc_amg_max_levels", c.opt_i("-pc_amg_max_levels", p.max_levels));
         p.cheby_ratio = c.opt_d("-" + prefix + "pc_amg_cheby_ratio", c.opt_d("-pc_amg_cheby_ratio", p.cheby_ratio));
+        p.power_its = c.opt_i("-" + prefix + "pc_amg_power_its", c.opt_i("-pc_amg_power_its", p.power_its));
+        if (cheb_only) {
+            p.max_levels = 1;
+            p.cheby_degree = c.opt_i("-" + prefix + "pc_amg_cheby_degree", 4);
+        }
         bool use_rbm = c.opt_i("-" + prefix + "pc_amg_rigid_body_modes", c.opt_i("-pc_amg_rigid_body_modes", 1)) != 0;
         if (bs > 1 && coords_host && coord_dim == bs && use_rbm) {
             std::vector<double> B;
@@ -149,6 +162,7 @@ KSP::~KSP() {
 }
 
 void KSP::op_apply(const double* x, double* y, SpmvMode mode, const double* z) {
+    ProfScope ps(*ctx, 0);
     if (!profile_op) { A->apply(x, y, mode, z); return; }
     if (ev_used + 2 > ev.size()) {
         for (int i = 0; i < 2; ++i) { cudaEvent_t e; PORO_CUDA(cudaEventCreate(&e)); ev.push_back(e); }
@@ -233,6 +247,7 @@ void KSP::solve_gmres(const double* b, double* x, bool flexible) {
             else if (rpc) { pc->apply(vj, w1.p); op_apply(w1.p, w); }
             else { op_apply(vj, w1.p); pc->apply(w1.p, w); }
             // classical Gram-Schmidt: one multi-dot pass, one multi-axpy(+norm) pass
+            ProfScope ps_gs(c, 5);
             vec_mdot(c, V.p, n, j + 1, w, n, d_h, false);
             allreduce_sum(c, d_h, j + 1);
             vec_maxpy_norm(c, w, V.p, n, j + 1, d_h, n, d_h + 2 * (m + 1));
@@ -382,9 +397,9 @@ void PCSchur::apply(const double* x, double* y) {
     const double* x0 = x + off0; const double* x1 = x + off1;
     double* y0 = y + off0; double* y1 = y + off1;
     if (fact == 0) {                       // lower: y0 = K0 x0 ; y1 = K1 (x1 - A10 y0)
-        k0->solve(x0, y0);
-        A10->apply(y0, t1.p, SPMV_SUB, x1);
-        k1->solve(t1.p, y1);
+        { ProfScope ps(c, 3); k0->solve(x0, y0); }
+        { ProfScope ps(c, 6); A10->apply(y0, t1.p, SPMV_SUB, x1); }
+        { ProfScope ps(c, 4); k1->solve(t1.p, y1); }
     } else if (fact == 1) {                // upper: y1 = K1 x1 ; y0 = K0 (x0 - A01 y1)
         k1->solve(x1, y1);
         A01->apply(y1, t0.p, SPMV_SUB, x0);
@@ -721,6 +736,7 @@ struct PhaseTimer {
 
 void PCBlockCC::apply(const double* x, double* y) {
     Ctx& c = *ctx;
+    ProfScope ps_pc(c, 1);
     PhaseTimer tt(c, timing, t_total);
     const int64_t ns = fl->n[0], nf = fl->n[1], np = fl->n[2];
     const double* xs = x + fl->off[0]; const double* xf = x + fl->off[1]; const double* xp = x + fl->off[2];
@@ -755,6 +771,7 @@ void PCBlockCC::apply(const double* x, double* y) {
     } else {
         {
             PhaseTimer t(c, timing, t_solid);
+            ProfScope ps(c, 2);
             ksp_s->solve(xs, ys);                                           // :221
         }
         {

@@ -38,6 +38,9 @@ struct MatOp : LinOp {
     struct Piece { HaloField* hf; int64_t x_off; int64_t ext_off; };
     std::vector<Piece> pieces;
     int64_t n_owned_cols = 0;
+    // node-blocked diagonal field blocks cut out of M and applied as BSR: y[row_off..] += B x[col_off..]
+    struct DiagPart { Csr B; int64_t row_off, col_off; };
+    std::vector<std::unique_ptr<DiagPart>> parts;
     DBuf<double> xext;
     int64_t rows() const override { return mat().nrows; }
     void apply(const double* x, double* y, SpmvMode mode = SPMV_SET, const double* z = nullptr) override;

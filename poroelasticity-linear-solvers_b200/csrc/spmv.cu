@@ -15,6 +15,7 @@
 // fallback for matrices with a row longer than kCap).
 // HBM-bound: algorithmic bytes = 12 nnz + 4 (nrows+1) + 8 nrows + 8 ncols.
 #include "common.cuh"
+#include "spmv_epilogue.cuh"
 #include <algorithm>
 
 namespace poro {
@@ -22,45 +23,7 @@ namespace poro {
 static constexpr int kSpmvBlock = 256;
 static constexpr int kNt = 8;                       // nonzeros per thread in the streaming phase
 static constexpr int kCap = kSpmvBlock * kNt;       // nonzeros per row block (16 KB of products)
-
-struct Epilogue {
-    int mode;                 // SpmvMode, or 3 = Chebyshev step, 4 = dot
-    const double* z;          // SUB/ADD source
-    // Chebyshev step
-    const double* d_old; double* d_new; double* r; double* xv; const double* dinv; double c1, c2;
-};
-
-template <int MODE>
-__device__ __forceinline__ double apply_epilogue(const Epilogue& ep, int row, double sum, const double* __restrict__ x,
-                                                 double* __restrict__ y) {
-    if (MODE == SPMV_SET) y[row] = sum;
-    else if (MODE == SPMV_SUB) y[row] = ep.z[row] - sum;
-    else if (MODE == SPMV_ADD) y[row] = ep.z[row] + sum;
-    else if (MODE == 3) {
-        const double rn = ep.r[row] - sum;
-        const double dn = ep.c1 * ep.d_old[row] + ep.c2 * ep.dinv[row] * rn;
-        ep.r[row] = rn;
-        ep.d_new[row] = dn;
-        ep.xv[row] += dn;
-    } else if (MODE == 4) {
-        y[row] = sum;
-        return sum * x[row];
-    }
-    return 0.0;
-}
-
-__device__ __forceinline__ double block_sum_256(double v, double* sm) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = 0.0;
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int w = 0; w < kSpmvBlock / 32; ++w) t += sm[w];
-    }
-    return t;
-}
+static constexpr int kMaxRows = 1024;               // rows per row block (row pointers and row sums live in shared memory)
 
 // ---------------------------------------------------------------------------------------------
 // CSR stream
@@ -71,10 +34,16 @@ __global__ void __launch_bounds__(kSpmvBlock) k_spmv_stream(const int* __restric
                                                             const double* __restrict__ x, double* __restrict__ y, Epilogue ep,
                                                             double* __restrict__ dot_partial) {
     __shared__ double prod[kCap];
+    __shared__ double rsum[kMaxRows];
+    __shared__ int rp[kMaxRows + 1];
     __shared__ double red[kSpmvBlock / 32];
     const int r0 = blk_row[blockIdx.x], r1 = blk_row[blockIdx.x + 1];
-    const int p0 = rowptr[r0];
-    const int cnt = rowptr[r1] - p0;
+    const int nr = r1 - r0;
+    // the block's slice of the row pointer, coalesced, once
+    for (int i = threadIdx.x; i <= nr; i += kSpmvBlock) rp[i] = rowptr[r0 + i];
+    __syncthreads();
+    const int p0 = rp[0];
+    const int cnt = rp[nr] - p0;
     const int* __restrict__ cb = col + p0;
     const double* __restrict__ vb = val + p0;
     // phase 1: stream the block's nonzeros; all matrix loads are issued before the first gather
@@ -95,18 +64,21 @@ __global__ void __launch_bounds__(kSpmvBlock) k_spmv_stream(const int* __restric
         if (i < cnt) prod[i] = v[t] * xv[t];
     }
     __syncthreads();
-    // phase 2: G lanes per row reduce from shared memory
+    // phase 2: G lanes per row reduce the products from shared memory into rsum
     const int lane = threadIdx.x & (G - 1);
     const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
-    double contrib = 0.0;
-    for (int row = r0 + threadIdx.x / G; row < r1; row += kSpmvBlock / G) {
-        const int a = rowptr[row] - p0, b = rowptr[row + 1] - p0;
+    for (int rl = threadIdx.x / G; rl < nr; rl += kSpmvBlock / G) {
+        const int a = rp[rl] - p0, b = rp[rl + 1] - p0;
         double s = 0.0;
         for (int i = a + lane; i < b; i += G) s += prod[i];
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) s += __shfl_down_sync(gmask, s, o, G);
-        if (lane == 0) contrib += apply_epilogue<MODE>(ep, row, s, x, y);
+        if (lane == 0) rsum[rl] = s;
     }
+    __syncthreads();
+    // phase 3: epilogue with consecutive threads on consecutive rows (coalesced, all latencies overlapped)
+    double contrib = 0.0;
+    for (int rl = threadIdx.x; rl < nr; rl += kSpmvBlock) contrib += apply_epilogue<MODE>(ep, r0 + rl, rsum[rl], x, y);
     if (MODE == 4) {
         double t = block_sum_256(contrib, red);
         if (threadIdx.x == 0) dot_partial[blockIdx.x] = t;
@@ -169,7 +141,7 @@ static void build_row_blocks(Ctx& c, const Csr& A) {
         const int limit = rp[r] + kCap;
         // largest r with rp[r] <= limit, but at most 8192 rows per block (keeps phase 2 short for empty rows)
         int hi = (int)(std::upper_bound(rp.begin() + r + 1, rp.end(), limit) - rp.begin()) - 1;
-        hi = std::min(hi, start + 8192);
+        hi = std::min(hi, start + kMaxRows);
         if (hi <= start) { ok = false; break; }      // a single row exceeds the block capacity
         r = hi;
     }
@@ -184,6 +156,20 @@ static void build_row_blocks(Ctx& c, const Csr& A) {
 template <int MODE>
 static int launch_spmv(Ctx& c, const Csr& A, const double* x, double* y, const Epilogue& ep, double* dot_partial) {
     if (A.nrows == 0) return 0;
+    if (A.block_hint > 1 && A.bsr_state < 0) {
+        // node-blocked matrix: convert once to BSR unless the blocks are mostly empty (e.g. M (x) I couplings)
+        auto B = std::make_shared<Bsr>();
+        int BS = A.block_hint % 3 == 0 ? 3 : (A.block_hint % 2 == 0 ? 2 : 0);
+        // break-even on bytes is a fill ratio of 12 / 8.44 = 1.42; below it BSR also wins on gather traffic
+        if (BS && c.opt_i("-poro_use_bsr", 1) && bsr_from_csr(c, A, BS, *B, c.opt_d("-poro_bsr_max_fill", 1.42))) {
+            A.bsr = B;
+            A.bsr_state = 1;
+        } else A.bsr_state = 0;
+        if (c.has_opt("-poro_verbose"))
+            fprintf(stderr, "    [spmv] %d x %d nnz=%lld hint=%d -> %s\n", A.nrows, A.ncols, (long long)A.nnz, A.block_hint,
+                    A.bsr_state == 1 ? "BSR" : "CSR");
+    }
+    if (A.bsr_state == 1) return bsr_launch<MODE>(c, *A.bsr, x, y, ep, dot_partial);
     if (A.nblk < 0) build_row_blocks(c, A);
     int grid;
     if (A.nblk > 0) {
@@ -254,7 +240,7 @@ void spmv_dot(Ctx& c, const Csr& A, const double* p, double* w, double* d_dot) {
     ep.mode = 4;
     if (A.nblk < 0) build_row_blocks(c, A);
     const int L = A.lanes ? A.lanes : 32;
-    const int64_t grid = A.nblk > 0 ? A.nblk : ceil_div((int64_t)A.nrows * L, kSpmvBlock);
+    const int64_t grid = A.nblk > 0 ? A.nblk : ceil_div((int64_t)A.nrows * L, kSpmvBlock);   // upper bound for BSR too
     if (grid <= Ctx::kScal) {
         int g = launch_spmv<4>(c, A, p, w, ep, c.d_scal);
         k_sum_to<<<1, 256, 0, c.stream>>>(c.d_scal, g, d_dot);
