@@ -338,6 +338,8 @@ struct Tick {
 
 // ---- set-up ---------------------------------------------------------------------------------
 void Amg::setup(Ctx& c, const Csr& A, int bs, const double* B_dev, int k, const AmgParams& p) {
+    // the hierarchy is built on this rank's owned block: its reductions must not be collective
+    struct LocalScope { Ctx& c; bool old; LocalScope(Ctx& c_) : c(c_), old(c_.local_only) { c.local_only = true; } ~LocalScope() { c.local_only = old; } } local_scope(c);
     ctx = &c;
     par = p;
     A0 = &A;

@@ -80,6 +80,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     int rank = 0, nranks = 1;
+    bool local_only = false;     // reductions stay on this rank (rank-local set-up such as the AMG power iteration)
     void* comm = nullptr;
     NcclApi* nccl = nullptr;
     std::map<std::string, std::string> opts;

@@ -304,7 +304,7 @@ void vec_maxpy_host(Ctx& c, double* y, const double* V, int64_t ld, int ncol, co
 // cross-rank sum + host read-back
 // ------------------------------------------------------------------------------------------
 void allreduce_sum(Ctx& c, double* d_vals, int k) {
-    if (c.nranks > 1) dist_allreduce_sum(c, d_vals, k);
+    if (c.nranks > 1 && !c.local_only) dist_allreduce_sum(c, d_vals, k);
 }
 
 void fetch(Ctx& c, const double* d_vals, int k, double* host) {
