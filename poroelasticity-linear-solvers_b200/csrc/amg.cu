@@ -461,7 +461,8 @@ void Amg::cheby(int l, const double* b, double* x, bool zero_guess) {
             if (need_r) r[i] = bi;
         });
     } else {
-        spmv(c, A, x, r, SPMV_SUB, b);
+        if (l == 0 && fine_mat) spmv(c, *fine_mat, fine_extend(x), r, SPMV_SUB, b);
+        else spmv(c, A, x, r, SPMV_SUB, b);
         pfor(c, n, [=] __device__(int64_t i) {
             double d = dinv[i] * r[i] * it;
             d_old[i] = d;
@@ -470,7 +471,8 @@ void Amg::cheby(int l, const double* b, double* x, bool zero_guess) {
     }
     for (int k = 1; k < deg; ++k) {
         double rho_new = 1.0 / (2.0 * sigma - rho);
-        spmv_cheb_step(c, A, d_old, d_new, r, x, dinv, rho_new * rho, 2.0 * rho_new / delta);
+        if (l == 0 && fine_mat) spmv_cheb_step(c, *fine_mat, fine_extend(d_old), d_old, d_new, r, x, dinv, rho_new * rho, 2.0 * rho_new / delta);
+        else spmv_cheb_step(c, A, d_old, d_old, d_new, r, x, dinv, rho_new * rho, 2.0 * rho_new / delta);
         rho = rho_new;
         std::swap(d_old, d_new);
     }
@@ -490,7 +492,8 @@ void Amg::cycle(int l, const double* b, double* x) {
     AmgLevel& L = *levels[l];
     AmgLevel& Ln = *levels[l + 1];
     cheby(l, b, x, true);
-    spmv(c, A, x, L.r.p, SPMV_SUB, b);
+    if (l == 0 && fine_mat) spmv(c, *fine_mat, fine_extend(x), L.r.p, SPMV_SUB, b);
+    else spmv(c, A, x, L.r.p, SPMV_SUB, b);
     spmv(c, L.R, L.r.p, Ln.b.p);
     cycle(l + 1, Ln.b.p, Ln.x.p);
     spmv(c, L.P, Ln.x.p, x, SPMV_ADD, x);

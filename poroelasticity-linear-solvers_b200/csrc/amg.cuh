@@ -1,6 +1,7 @@
 // amg.cuh -- smoothed-aggregation AMG hierarchy (device set-up + V-cycle).
 #pragma once
 #include "common.cuh"
+#include <functional>
 
 namespace poro {
 
@@ -29,6 +30,10 @@ struct Amg {
     const Csr* A0 = nullptr;        // finest operator is borrowed
     DBuf<double> coarse_inv;
     bool coarse_direct = false;
+    // row-partitioned runs: level-0 smoothing and residuals use the TRUE distributed operator (local rows x
+    // [owned | halo] columns) after a halo exchange; the transfer operators and coarse levels stay rank-local
+    const Csr* fine_mat = nullptr;
+    std::function<const double*(const double*)> fine_extend;
     int prof_base = -1;             // phase-profile slot of level 0 (-1: not profiled)
 
     // B: device n x k row-major near-nullspace (may be null -> one constant per component)

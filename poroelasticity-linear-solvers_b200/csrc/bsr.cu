@@ -9,7 +9,7 @@
 //
 // Layout: values are interleaved in groups of 32 blocks, val[((p / 32) * BS^2 + e) * 32 + p % 32]
 // for entry e of block p, so that "one thread per block" reads every entry fully coalesced.
-// Kernel: a CTA streams up to kCapB blocks of whole block rows (thread per block, kNtb blocks per
+// Kernel: a CTA streams up to 256 * kNtb blocks of whole block rows (thread per block, kNtb blocks per
 // thread in flight), writes BS partial sums per block to shared memory, then G lanes per block
 // row reduce them and apply the same epilogues as the CSR kernel (y = Ax, z - Ax, z + Ax, fused
 // Chebyshev step, fused p.Ap).
@@ -21,16 +21,14 @@
 namespace poro {
 
 static constexpr int kBlk = 256;
-static constexpr int kNtb = 2;
-static constexpr int kCapB = kBlk * kNtb;
 static constexpr int kMaxBRows = 256;     // block rows per chunk (row pointers and row sums live in shared memory)
 
-template <int BS, int G, int MODE, bool DIAG>
+template <int BS, int G, int MODE, bool DIAG, int kNtb>
 __global__ void __launch_bounds__(kBlk) k_bsr_stream(const int* __restrict__ blk_row, const int* __restrict__ rowptr,
                                                      const int* __restrict__ col, const double* __restrict__ val,
                                                      const double* __restrict__ x, double* __restrict__ y, Epilogue ep,
                                                      double* __restrict__ dot_partial) {
-    __shared__ double part[kCapB * BS];
+    __shared__ double part[kBlk * kNtb * BS];
     __shared__ double rsum[kMaxBRows * BS];
     __shared__ int rp[kMaxBRows + 1];
     __shared__ double red[kBlk / 32];
@@ -183,15 +181,22 @@ bool bsr_from_csr(Ctx& c, const Csr& A, int BS, Bsr& out, double max_fill) {
             }
         });
     }
-    // pack whole block rows into chunks of at most kCapB blocks
+    // pack whole block rows into chunks of at most 256 * ntb blocks
     std::vector<int> rp((size_t)nbr + 1);
     PORO_CUDA(cudaMemcpyAsync(rp.data(), out.rowptr.p, rp.size() * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
     PORO_CUDA(cudaStreamSynchronize(c.stream));
+    int max_row = 0;
+    for (int i = 0; i < nbr; ++i) max_row = std::max(max_row, rp[i + 1] - rp[i]);
+    // dense blocks: one block per thread keeps 7 CTAs per SM resident; long block rows (coarse levels) need two
+    // measured on B200 (profiles/r1_spmv_kernels.md): 2 blocks per thread beats 1 (0.126 vs 0.140 ms on A_ss) and,
+    // for diagonal blocks, 4 (0.086 vs 0.105 ms on A_sf)
+    out.ntb = 2;
+    (void)max_row;
     std::vector<int> blk;
     int r = 0;
     while (r < nbr) {
         blk.push_back(r);
-        const int limit = rp[r] + kCapB;
+        const int limit = rp[r] + kBlk * out.ntb;
         int hi = (int)(std::upper_bound(rp.begin() + r + 1, rp.end(), limit) - rp.begin()) - 1;
         hi = std::min(hi, r + kMaxBRows);
         if (hi <= r) return false;                 // one block row longer than a chunk
@@ -211,8 +216,9 @@ int bsr_launch(Ctx& c, const Bsr& B, const double* x, double* y, const Epilogue&
     const int G = a <= 1.5 ? 1 : a <= 4 ? 2 : a <= 12 ? 4 : a <= 48 ? 8 : a <= 160 ? 16 : 32;
 #define GO(BSS, GG)                                                                                                          \
     do {                                                                                                                     \
-        if (B.diag_only) k_bsr_stream<BSS, GG, MODE, true><<<B.nblk, kBlk, 0, c.stream>>>(B.blk_row.p, B.rowptr.p, B.col.p, B.val.p, x, y, ep, dot_partial); \
-        else k_bsr_stream<BSS, GG, MODE, false><<<B.nblk, kBlk, 0, c.stream>>>(B.blk_row.p, B.rowptr.p, B.col.p, B.val.p, x, y, ep, dot_partial);          \
+        if (B.diag_only) k_bsr_stream<BSS, GG, MODE, true, 2><<<B.nblk, kBlk, 0, c.stream>>>(B.blk_row.p, B.rowptr.p, B.col.p, B.val.p, x, y, ep, dot_partial); \
+        else if (B.ntb == 1) k_bsr_stream<BSS, GG, MODE, false, 1><<<B.nblk, kBlk, 0, c.stream>>>(B.blk_row.p, B.rowptr.p, B.col.p, B.val.p, x, y, ep, dot_partial); \
+        else k_bsr_stream<BSS, GG, MODE, false, 2><<<B.nblk, kBlk, 0, c.stream>>>(B.blk_row.p, B.rowptr.p, B.col.p, B.val.p, x, y, ep, dot_partial);          \
     } while (0)
 #define GOG(BSS) switch (G) { case 1: GO(BSS, 1); break; case 2: GO(BSS, 2); break; case 4: GO(BSS, 4); break; \
                               case 8: GO(BSS, 8); break; case 16: GO(BSS, 16); break; default: GO(BSS, 32); break; }

@@ -408,6 +408,12 @@ static std::unique_ptr<KSP> make_inner(poro_ctx* h, MatOp* op, const std::string
         k->owned_pc = make_pc(c, pt, *src, bs, coords, cdim, prefix);
     }
     k->pc = k->owned_pc.get();
+    if (PCAmg* a = dynamic_cast<PCAmg*>(k->pc)) {
+        if (c.nranks > 1 && op->mat().ncols != op->mat().nrows && c.opt_i("-poro_amg_distributed_smoother", 1)) {
+            a->amg.fine_mat = &op->mat();
+            a->amg.fine_extend = [op](const double* v) { return op->extended(v); };
+        }
+    }
     if (PCAmg* a = dynamic_cast<PCAmg*>(k->pc))
         a->amg.prof_base = prefix == "s_" ? 8 : (bs > 1 ? 16 : (prefix.find("fieldsplit") != std::string::npos ? 24 : -1));
     return k;

@@ -161,6 +161,7 @@ inline int stream_grid(const Ctx& c, int64_t n, int block, int per_thread = 4, i
 struct Bsr {
     int bs = 0, nbrows = 0, nbcols = 0;
     int64_t nnzb = 0;
+    int ntb = 1;                // blocks per thread of the stream kernel (chunk capacity = 256 * ntb)
     bool diag_only = false;     // blocks are diagonal (e.g. M (x) I couplings): BS values per block instead of BS^2
     DBuf<int> rowptr, col;
     DBuf<double> val;
@@ -217,7 +218,7 @@ enum SpmvMode { SPMV_SET = 0, SPMV_SUB = 1, SPMV_ADD = 2 };   // y = Ax | y = z 
 void csr_choose_lanes(Csr& A);
 void spmv(Ctx& c, const Csr& A, const double* x, double* y, SpmvMode mode = SPMV_SET, const double* z = nullptr);
 // fused Chebyshev step: t = A d_old; r -= t; d_new = c1 d_old + c2 dinv.*r; x += d_new
-void spmv_cheb_step(Ctx& c, const Csr& A, const double* d_old, double* d_new, double* r, double* x,
+void spmv_cheb_step(Ctx& c, const Csr& A, const double* x_in, const double* d_old, double* d_new, double* r, double* x,
                     const double* dinv, double c1, double c2);
 // w = A p and *d_dot += p . w (local partial; d_dot must be zeroed by caller)
 void spmv_dot(Ctx& c, const Csr& A, const double* p, double* w, double* d_dot);

@@ -212,12 +212,12 @@ void spmv(Ctx& c, const Csr& A, const double* x, double* y, SpmvMode mode, const
     else launch_spmv<SPMV_ADD>(c, A, x, y, ep, nullptr);
 }
 
-void spmv_cheb_step(Ctx& c, const Csr& A, const double* d_old, double* d_new, double* r, double* x,
+void spmv_cheb_step(Ctx& c, const Csr& A, const double* x_in, const double* d_old, double* d_new, double* r, double* x,
                     const double* dinv, double c1, double c2) {
     Epilogue ep{};
     ep.mode = 3;
     ep.d_old = d_old; ep.d_new = d_new; ep.r = r; ep.xv = x; ep.dinv = dinv; ep.c1 = c1; ep.c2 = c2;
-    launch_spmv<3>(c, A, d_old, nullptr, ep, nullptr);
+    launch_spmv<3>(c, A, x_in, nullptr, ep, nullptr);      // x_in = d_old, or its [owned | halo] extension
 }
 
 __global__ void k_sum_to(const double* __restrict__ partial, int n, double* __restrict__ out) {
