@@ -110,7 +110,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def oracle_solver(sys_, par, max_it):
+def oracle_solver(sys_, par, max_it, threaded=True):
     """The CPU port of the benchmarked algorithm (same options as BENCH_OPTIONS)."""
     from oracle.amg import SAAMG, rigid_body_modes
     from oracle.blockpc import BlockPC, SchurLower, krylov_solver
@@ -123,6 +123,10 @@ def oracle_solver(sys_, par, max_it):
     mkfp = lambda M: SchurLower(M, sys_.nf, sys_.np_, krylov_solver("preonly", cheb_f), krylov_solver("preonly", amg_p), "f")
     pc = BlockPC(sys_, {"s": krylov_solver("preonly", amg_s), "fp": mkfp})
     A = sys_.A
+    if threaded:
+        from oracle import fastmat
+        fastmat.accelerate(pc)          # every `M @ x` of the timed loop -> OpenMP CSR kernel (oracle/csrc/omp_kernels.c)
+        A = fastmat.OmpCsr(A)
 
     def run():
         return gmres(lambda v: A @ v, sys_.b, pc, rtol=RTOL, atol=0.0, dtol=1e20, max_it=max_it, restart=max(max_it, 1),
@@ -132,23 +136,36 @@ def oracle_solver(sys_, par, max_it):
 
 def cpu_baseline(sample_n: int, budget_s: float = 20.0):
     """Oracle port timed on the host cores on a bounded sample: the same problem on a smaller
-    mesh (the metric is normalised per DoF x iteration)."""
+    mesh (the metric is normalised per DoF x iteration).  Both the plain scipy build (1 thread) and the
+    OpenMP-matvec build (all host threads) are timed; the faster one is reported with its thread count."""
+    from oracle import fastmat
     from oracle.problems import swelling
     sys_, par = swelling(3, sample_n, "diagonal")
-    run = oracle_solver(sys_, par, 100)
-    t0 = time.perf_counter()
-    r = run()
-    dt = time.perf_counter() - t0
-    reps = 1
-    while dt < budget_s / 4 and reps < 8:
-        t0 = time.perf_counter()
-        r = run()
-        dt = min(dt, time.perf_counter() - t0)
-        reps += 1
-    return {"value": sys_.n * r.its / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "same problem on mesh N=%d (%d DoFs), full solve to rtol 1e-8: %d its in %.2f s, "
-                      "numpy/scipy single thread; NOT PETSc/hypre" % (sample_n, sys_.n, r.its, dt),
-            "its": r.its, "seconds": dt}
+    best = None
+    for threaded in (False, True):
+        run = oracle_solver(sys_, par, 100, threaded=threaded)
+        dt, r = None, None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            r = run()
+            d = time.perf_counter() - t0
+            dt = d if dt is None else min(dt, d)
+            if d > budget_s / 4:
+                break
+        cores = fastmat.threads() if threaded else 1
+        cand = {"value": sys_.n * r.its / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "same problem on mesh N=%d (%d DoFs), full solve to rtol 1e-8: %d its in %.2f s; %s; NOT PETSc/hypre"
+                          % (sample_n, sys_.n, r.its, dt, "numpy + OpenMP CSR matvec on %d threads" % cores if threaded
+                             else "numpy/scipy, 1 thread"),
+                "its": r.its, "seconds": dt}
+        if best is None or cand["value"] > best["value"]:
+            best = cand
+    return best
+
+
+def _threads():
+    from oracle import fastmat
+    return fastmat.threads()
 
 
 def run_reference(args):
@@ -158,9 +175,14 @@ def run_reference(args):
     from oracle.problems import swelling
     sample_n = args.cpu_sample_n
     sys_, par = swelling(3, sample_n, "diagonal")
-    run = oracle_solver(sys_, par, 100)
-    for _ in range(min(args.warmup, 1)):
-        run()
+    # pick the faster of the two CPU builds (scipy single thread / OpenMP matvec on all host threads)
+    from oracle import fastmat
+    cand = []
+    for threaded in (False, True):
+        rr = oracle_solver(sys_, par, 100, threaded=threaded)
+        t0 = time.perf_counter(); rr(); cand.append((time.perf_counter() - t0, threaded, rr))
+    _, threaded, run = min(cand, key=lambda c: c[0])
+    ncores = fastmat.threads() if threaded else 1
     t0 = time.perf_counter()
     its = 0
     for _ in range(args.steps):
@@ -172,8 +194,9 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "swelling-3d.py, GMRES(right) + block diagonal PC + SA-AMG, rtol 1e-8; CPU oracle port "
                                    "on a bounded sample mesh N=%d (%d DoFs)" % (sample_n, sys_.n)},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": "mesh N=%d (%d DoFs), %d full solves" % (sample_n, sys_.n, args.steps)},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "port",
+                             "sample": "mesh N=%d (%d DoFs), %d full solves, %s; NOT PETSc/hypre" % (
+                                 sample_n, sys_.n, args.steps, "numpy + OpenMP CSR matvec" if threaded else "numpy/scipy 1 thread")},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))

@@ -497,7 +497,7 @@ void Amg::cycle(int l, const double* b, double* x) {
     spmv(c, L.R, L.r.p, Ln.b.p);
     cycle(l + 1, Ln.b.p, Ln.x.p);
     spmv(c, L.P, Ln.x.p, x, SPMV_ADD, x);
-    cheby(l, b, x, false);
+    if (par.post_smooth) cheby(l, b, x, false);
 }
 
 void Amg::apply(const double* b, double* x) { cycle(0, b, x); }

@@ -12,6 +12,7 @@ struct AmgParams {
     int cheby_degree = 2;
     double cheby_ratio = 10.0;
     int power_its = 15;
+    int post_smooth = 1;        // 0: V(nu,0) cycle (non-symmetric: only under GMRES/FGMRES)
 };
 
 struct AmgLevel {

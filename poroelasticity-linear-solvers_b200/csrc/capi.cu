@@ -488,7 +488,11 @@ int poro_pc_setup(poro_ctx* h, poro_mat* A, poro_mat* P, poro_mat* P_diff, const
         cc.Mfp_s = extract_block(h, *Pp, of, of + nf + np, {0});
         // fp solver: lib/Preconditioner.py:135-138: LU on the whole block, or GMRES + fieldsplit then options
         std::string fp_pc = ipc == "lu" ? "lu" : c.opt("-fp_pc_type", "fieldsplit");
-        if (fp_pc != "fieldsplit") {
+        // an "exact" fp block too large for the dense inverse: the fp block is a non-symmetric saddle-type matrix on
+        // which AMG is meaningless, so iterate GMRES on it to 1e-12 with a full Schur factorisation whose sub-blocks
+        // are themselves exact (dense) or tightly iterated
+        const bool fp_exact_big = fp_pc == "lu" && (nf + np) > c.opt_i("poro_dense_lu_limit", 8192);
+        if (fp_pc != "fieldsplit" && !fp_exact_big) {
             cc.Mfp_fp = extract_block(h, *Pp, of, of + nf + np, {1, 2});
             cc.ksp_fp = make_inner(h, cc.Mfp_fp.get(), ipc == "lu" ? iksp : "gmres", fp_pc, "fp_", 1, nullptr, 0);
         } else {
@@ -496,11 +500,14 @@ int poro_pc_setup(poro_ctx* h, poro_mat* A, poro_mat* P, poro_mat* P_diff, const
             k->ctx = &c;
             k->type = "gmres";
             k->set_from_options("fp_");
+            if (fp_exact_big) {
+                k->type = "gmres"; k->rtol = 1e-12; k->atol = 1e-300; k->max_it = 400; k->restart = 200; k->right = true;
+            }
             auto sch = std::make_unique<PCSchur>();
             sch->ctx = &c;
-            std::string order = c.opt("-fp_pc_fieldsplit_order", "pf");            // "pf" = reference (Preconditioner.py:113-114)
+            std::string order = c.opt("-fp_pc_fieldsplit_order", fp_exact_big ? "fp" : "pf");   // "pf" = reference (Preconditioner.py:113-114)
             sch->p_first = order != "fp";
-            std::string fact = c.opt("-fp_pc_fieldsplit_schur_fact_type", "lower");
+            std::string fact = c.opt("-fp_pc_fieldsplit_schur_fact_type", fp_exact_big ? "full" : "lower");
             sch->fact = fact == "lower" ? 0 : fact == "upper" ? 1 : fact == "full" ? 2 : fact == "diag" ? 3 : -1;
             PORO_REQUIRE(sch->fact >= 0, "unknown -fp_pc_fieldsplit_schur_fact_type");
             const int t0 = sch->p_first ? 2 : 1, t1 = sch->p_first ? 1 : 2;
@@ -543,10 +550,11 @@ int poro_pc_setup(poro_ctx* h, poro_mat* A, poro_mat* P, poro_mat* P_diff, const
                 csr_add_scaled(c, a11, prod, -1.0, nullptr, sch->S->M);
             }
             const int bs0 = t0 == 1 ? bs_v : 1, bs1 = t1 == 1 ? bs_v : 1;
-            sch->k0 = make_inner(h, sch->A00.get(), "preonly", "amg", "fp_fieldsplit_0_", bs0, t0 == 1 ? cs : nullptr, t0 == 1 ? cdim : 0);
+            const char* sub_pc = fp_exact_big ? "lu" : "amg";
+            sch->k0 = make_inner(h, sch->A00.get(), "preonly", sub_pc, "fp_fieldsplit_0_", bs0, t0 == 1 ? cs : nullptr, t0 == 1 ? cdim : 0);
             // K1: operator A11 (PETSc applies the Schur operator matrix-free for Krylov K1; with preonly only the PC matters),
             // preconditioner built from the assembled selfp matrix
-            sch->k1 = make_inner(h, sch->S.get(), "preonly", "amg", "fp_fieldsplit_1_", bs1, t1 == 1 ? cs : nullptr, t1 == 1 ? cdim : 0);
+            sch->k1 = make_inner(h, sch->S.get(), "preonly", sub_pc, "fp_fieldsplit_1_", bs1, t1 == 1 ? cs : nullptr, t1 == 1 ? cdim : 0);
             sch->t0.alloc((size_t)sch->n0); sch->t1.alloc((size_t)sch->n1); sch->u0.alloc((size_t)sch->n0);
             cc.schur = sch.get();
             k->owned_pc = std::move(sch);

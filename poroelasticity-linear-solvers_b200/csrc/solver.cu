@@ -101,6 +101,7 @@ std::unique_ptr<PC> make_pc(Ctx& c, const std::string& pc_type, const Csr& A, in
         p.coarse_size = c.opt_i("-" + prefix + "pc_amg_coarse_size", c.opt_i("-pc_amg_coarse_size", p.coarse_size));
         p.max_levels = c.opt_i("-" + prefix + "pc_amg_max_levels", c.opt_i("-pc_amg_max_levels", p.max_levels));
         p.cheby_ratio = c.opt_d("-" + prefix + "pc_amg_cheby_ratio", c.opt_d("-pc_amg_cheby_ratio", p.cheby_ratio));
+        p.post_smooth = c.opt_i("-" + prefix + "pc_amg_post_smooth", c.opt_i("-pc_amg_post_smooth", p.post_smooth));
         p.power_its = c.opt_i("-" + prefix + "pc_amg_power_its", c.opt_i("-pc_amg_power_its", p.power_its));
         if (cheb_only) {
             p.max_levels = 1;

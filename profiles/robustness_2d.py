@@ -1,0 +1,42 @@
+"""BASELINE config 3 on the GPU: the mesh-size robustness sweep of paper-scripts/robustness_2d.sh
+(swelling.py -N {10,20,40,80[,160]} x {2-way 'diagonal', 3-way 'diagonal 3-way'} x {exact, AMG}),
+one time step each, rtol 1e-6 / atol 1e-8 / maxiter 500 as in swelling.py:64-66.
+
+exact  = petsc-options-exact semantics (dense inverse up to 8192 rows per block, GMRES+AMG to 1e-12 beyond)
+amg    = linear AMG preconditioner (one V-cycle per block, pressure Schur), right-preconditioned GMRES
+    python profiles/robustness_2d.py [maxN]
+"""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+from helpers import AMG_OPTIONS, EXACT_OPTIONS, gpu_solve
+from oracle.problems import swelling
+
+AMG3 = AMG_OPTIONS + """
+-f_ksp_type preonly
+-f_pc_type hypre
+-p_ksp_type preonly
+-p_pc_type hypre
+-diff_ksp_type preonly
+-diff_pc_type hypre
+"""
+maxN = int(sys.argv[1]) if len(sys.argv) > 1 else 80
+print("%-4s %-16s %-6s %8s %5s %7s %10s %10s" % ("N", "pc type", "inner", "DoFs", "its", "reason", "solve ms", "true res"))
+for N in [n for n in (10, 20, 40, 80, 160) if n <= maxN]:
+    for pct in ("diagonal", "diagonal 3-way"):
+        s, par = swelling(2, N, pct)
+        for name, opts in (("exact", EXACT_OPTIONS), ("amg", AMG3)):
+            if name == "exact" and N > 40:
+                continue
+            t0 = time.perf_counter()
+            g = gpu_solve(s, par, opts)
+            t_all = time.perf_counter() - t0
+            # second solve for timing (first includes set-up)
+            ksp = g["solver"].solver
+            from poro_b200.lib.backend import DeviceVector, get_context
+            ctx = get_context(0)
+            db, dx = DeviceVector(s.b, ctx=ctx), DeviceVector(n=s.n, ctx=ctx)
+            ctx.sync(); t0 = time.perf_counter(); ksp.solve(db, dx); ctx.sync(); dt = time.perf_counter() - t0
+            res = np.linalg.norm(s.b - s.A @ dx.numpy()) / np.linalg.norm(s.b)
+            print("%-4d %-16s %-6s %8d %5d %7d %10.2f %10.2e" % (N, pct, name, s.n, ksp.its, ksp.reason, 1e3 * dt, res), flush=True)
