@@ -325,6 +325,14 @@ def main():
         return
     peak, peak_src = peaks()
     achieved = (op_bytes / 1e9) / (op_ms / 1e3 / max(op_calls, 1)) if op_calls else None
+    # dominant kernel = k_bsr_stream on the solid block: its launch inside the outer operator (slot 33 = A_ss part,
+    # y_s += A_ss x_s), timed live by CUDA events on the library's stream during the timed solves
+    parts = ksp.parts_info()
+    dom = None
+    if len(parts) > 1 and 33 in phases and phases[33][1] > 0:
+        ms33, n33 = phases[33]
+        dom = {"bytes": parts[1][0], "format": {0: "CSR", 1: "BSR3", 2: "diag-BSR3"}[parts[1][1]], "avg_ms": ms33 / n33, "launches": n33,
+               "achieved": parts[1][0] / 1e9 / (ms33 / n33 / 1e3)}
     stats = pc.getPythonContext().stats()
     line = {
         "metric": METRIC, "value": n_global * its / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -344,10 +352,18 @@ def main():
         "gpu_launches": int(launches),
         "phases_ms_per_solve": {PHASE_NAMES.get(k, str(k)): round(v[0] / args.steps, 3) for k, v in sorted(phases.items())},
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "outer operator y = A x: k_bsr_stream<3> (A_ss, A_ff, diagonal-block A_sf, A_fs) + k_spmv_stream (CSR remainder)", "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
-                     "peak_source": peak_src, "bytes_per_launch": op_bytes, "launches_timed": op_calls,
-                     "avg_launch_ms": op_ms / max(op_calls, 1), "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None},
+        "roofline": ({"bound": "hbm", "kernel": "k_bsr_stream<3,8,ADD> on A_ss (y_s += A_ss x_s inside the outer operator product)",
+                      "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["achieved"] / peak,
+                      "traffic": 716.5e6 if abs(dom["bytes"] - 7.32e8) < 5e7 else None,
+                      "traffic_note": "dram__bytes_read+write of this kernel on this matrix from ncu --set full (profiles/r1_spmv_kernels.md); null for other meshes",
+                      "peak_source": peak_src, "bytes_per_launch": dom["bytes"], "format": dom["format"], "launches_timed": dom["launches"],
+                      "avg_launch_ms": dom["avg_ms"], "frac_of_nominal_8TBs": dom["achieved"] / 8000.0} if dom else
+                     {"bound": "hbm", "kernel": "k_spmv_stream (outer operator y = A x)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                      "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                      "bytes_per_launch": op_bytes, "launches_timed": op_calls, "avg_launch_ms": op_ms / max(op_calls, 1)}),
+        "outer_operator": {"launches_per_product": len(parts), "bytes_per_product": op_bytes, "avg_ms": op_ms / max(op_calls, 1),
+                           "achieved_GBs": achieved, "frac": (achieved / peak) if achieved else None,
+                           "parts": [{"bytes": b, "format": {0: "CSR", 1: "BSR3", 2: "diag-BSR3"}[f]} for b, f in parts]},
     }
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args.cpu_sample_n)

@@ -132,6 +132,9 @@ int poro_pc_amg_info(poro_pc* pc, const char* name, int64_t* rows, int64_t* nnz,
  * 0 stops, -1 only reads.  op_bytes = algorithmic bytes of one product
  * (12 nnz + 4 (nrows+1) + 8 nrows + 8 ncols). */
 int poro_ksp_profile(poro_ksp* ksp, int enable, double* op_ms, int64_t* op_calls, int64_t* op_bytes);
+/* algorithmic bytes of every launch of the outer operator product: [CSR remainder, node-blocked part 0, 1, ...]
+ * (format flag 0 CSR, 1 BSR, 2 diagonal-block BSR); matches phase-profile slots 32, 33, ... */
+int poro_ksp_parts_info(poro_ksp* ksp, int64_t* bytes, int* format, int cap, int* n);
 /* phase profile (CUDA events on the launching stream): slots 0 outer operator, 1 preconditioner apply,
  * 2 solid solve, 3 fp split 0, 4 fp split 1, 5 orthogonalisation, 6 fp coupling product,
  * 8+l / 16+l / 24+l AMG level l (inclusive) of the s / f / p hierarchies.  enable as in poro_ksp_profile. */

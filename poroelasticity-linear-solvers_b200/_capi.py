@@ -59,6 +59,7 @@ SIGNATURES = {
     "poro_ksp_mult": [vp, vp, vp],
     "poro_ksp_profile": [vp, C.c_int, c_f64p, c_i64p, c_i64p],
     "poro_profile": [vp, C.c_int, c_f64p, c_i64p, C.c_int],
+    "poro_ksp_parts_info": [vp, c_i64p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)],
 }
 
 

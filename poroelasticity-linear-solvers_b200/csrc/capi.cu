@@ -806,6 +806,31 @@ int poro_ksp_profile(poro_ksp* k, int enable, double* op_ms, int64_t* op_calls, 
     API_END
 }
 
+// algorithmic bytes of each launch of the outer operator: [CSR remainder, part 0, part 1, ...]; returns count in *n
+int poro_ksp_parts_info(poro_ksp* k, int64_t* bytes, int* is_bsr, int cap, int* n) {
+    API_BEGIN
+    std::vector<int64_t> b;
+    std::vector<int> f;
+    const Csr& A = k->A->mat();
+    b.push_back(12 * A.nnz + 4 * ((int64_t)A.nrows + 1) + 8 * (int64_t)A.nrows + 8 * (int64_t)A.ncols);
+    f.push_back(0);
+    for (auto& p : k->A->parts) {
+        const Csr& B = p->B;
+        if (B.bsr_state == 1) {
+            const Bsr& bb = *B.bsr;
+            const int64_t ne = bb.diag_only ? bb.bs : bb.bs * bb.bs;
+            b.push_back((8 * ne + 4) * bb.nnzb + 4 * ((int64_t)bb.nbrows + 1) + 16 * (int64_t)B.nrows + 8 * (int64_t)B.ncols);
+            f.push_back(bb.diag_only ? 2 : 1);
+        } else {
+            b.push_back(12 * B.nnz + 4 * ((int64_t)B.nrows + 1) + 16 * (int64_t)B.nrows + 8 * (int64_t)B.ncols);
+            f.push_back(0);
+        }
+    }
+    *n = (int)b.size();
+    for (int i = 0; i < *n && i < cap; ++i) { bytes[i] = b[i]; is_bsr[i] = f[i]; }
+    API_END
+}
+
 int poro_profile(poro_ctx* h, int enable, double* ms, int64_t* calls, int n) {
     API_BEGIN
     Ctx& c = h->c;
