@@ -241,7 +241,7 @@ def main():
         prob = distributed_problem(3, N, "diagonal", rank, world, ctx)
         sys_, par, n_global = prob.sys, prob.par, prob.n_global
     else:
-        from oracle.problems import swelling      # host assembler = test infrastructure standing in for FEniCS
+        from hostfem.problems import swelling     # host-side input generation standing in for FEniCS assembly (not the oracle)
         sys_, par = swelling(3, N, "diagonal")
         n_global = sys_.n
     t_asm = time.perf_counter() - t_asm

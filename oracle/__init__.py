@@ -14,10 +14,8 @@ the Krylov restatements, and the per-function file:line citations.
 
 Modules
 -------
-fem        meshes (dolfin UnitSquareMesh/UnitCubeMesh connectivity), P2^d x P2^d x P1
-           assembly of A, P, P_diff, b (lib/Assembler.py:66-221, :235-270) and
-           DirichletBC.apply (lib/Poromechanics.py:76-83)
-problems   the driver configs (swelling.py, swelling-3d.py, footing.py)
+fem, problems   re-exports of hostfem/ (the host-side assembler and driver configs: input generation that
+                stands in for FEniCS, shared by bench.py, the tests and this oracle; not part of the solve path)
 krylov     PETSc-semantics GMRES / CG / preonly restatements (lib/Solver.py:92-102)
 blockpc    PreconditionerCC.apply 2-way / 3-way (lib/Preconditioner.py:141-250)
 aar        AAR.solve incl. its quirks (lib/AAR.py:46-137)

@@ -389,6 +389,7 @@ static std::unique_ptr<KSP> make_inner(poro_ctx* h, MatOp* op, const std::string
             holder->ctx = &c;
             local_square(c, *op, holder->M);
             csr_choose_lanes(holder->M);
+            holder->M.block_hint = bs;
             src = &holder->M;
         }
         k->owned_pc = make_pc(c, pt, *src, bs, coords, cdim, prefix);
@@ -457,7 +458,7 @@ int poro_pc_setup(poro_ctx* h, poro_mat* A, poro_mat* P, poro_mat* P_diff, const
     const double* cs = fl.coords_s.empty() ? nullptr : fl.coords_s.data();
     const int cdim = fl.coord_dim;
     cc.Ms_s = extract_block(h, *Pp, os, os + ns, {0});
-    if (c.nranks == 1) cc.Ms_s->M.block_hint = bs_v;
+    cc.Ms_s->M.block_hint = bs_v;          // also with halo columns: any grouping of columns in triples is valid
     cc.ksp_s = make_inner(h, cc.Ms_s.get(), iksp, ipc, "s_", bs_v, cs, cdim);
     cc.t_s.alloc(ns); cc.t_f.alloc(nf); cc.t_p.alloc(np); cc.t_fp.alloc(nf + np);
     if (cc.three_way) {
@@ -465,7 +466,7 @@ int poro_pc_setup(poro_ctx* h, poro_mat* A, poro_mat* P, poro_mat* P_diff, const
         cc.Ms_f = extract_block(h, *Pp, os, os + ns, {1});
         cc.Ms_p = extract_block(h, *Pp, os, os + ns, {2});
         cc.Mf_f = extract_block(h, *Pp, of, of + nf, {1});
-        if (c.nranks == 1) cc.Mf_f->M.block_hint = bs_v;
+        cc.Mf_f->M.block_hint = bs_v;
         cc.Mf_p = extract_block(h, *Pp, of, of + nf, {2});
         cc.Mp_p = extract_block(h, *Pp, op_, op_ + np, {2});
         {
@@ -518,7 +519,7 @@ int poro_pc_setup(poro_ctx* h, poro_mat* A, poro_mat* P, poro_mat* P_diff, const
             sch->A01 = extract_block(h, *Pp, fl.off[t0], fl.off[t0] + fl.n[t0], {t1});
             sch->A10 = extract_block(h, *Pp, fl.off[t1], fl.off[t1] + fl.n[t1], {t0});
             sch->A11 = extract_block(h, *Pp, fl.off[t1], fl.off[t1] + fl.n[t1], {t1});
-            if (c.nranks == 1) (t0 == 1 ? sch->A00 : sch->A11)->M.block_hint = bs_v;
+            (t0 == 1 ? sch->A00 : sch->A11)->M.block_hint = bs_v;
             // selfp: S = A11 - A10 diag(A00)^-1 A01 on the local (owned) parts
             {
                 Csr a00, a01, a10, a11;

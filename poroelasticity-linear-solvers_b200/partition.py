@@ -146,8 +146,8 @@ def _gather_fn(world):
 def distributed_problem(dim: int, N: int, pc_type: str, rank: int, world: int, ctx=None, overrides=None) -> DistributedProblem:
     """Assemble this rank's z-slab of the 3D swelling problem and install the halo plan on `ctx`."""
     assert dim == 3, "slab partition is implemented for the structured cube"
-    from oracle.fem import PoroAssembler, unit_cube_mesh     # host assembler (stands in for FEniCS)
-    from oracle.problems import _traction, swelling_params
+    from hostfem.fem import PoroAssembler, unit_cube_mesh    # host assembler (stands in for FEniCS; not the oracle)
+    from hostfem.problems import _traction, swelling_params
     par = swelling_params(3)
     if overrides:
         par.update(overrides)

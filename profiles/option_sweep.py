@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
 from bench import BENCH_OPTIONS, PHASE_NAMES
-from oracle.problems import swelling
+from hostfem.problems import swelling
 from poro_b200.lib.backend import DeviceMatrix, DeviceVector, get_context
 from poro_b200.lib.IndexSet import IndexSet
 from poro_b200.lib.Parser import load_petsc_options

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from helpers import AMG_OPTIONS, EXACT_OPTIONS, gpu_solve
-from oracle.problems import swelling
+from hostfem.problems import swelling
 
 AMG3 = AMG_OPTIONS + """
 -f_ksp_type preonly

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
 import torch
-from oracle.problems import swelling
+from hostfem.problems import swelling
 from poro_b200.lib.backend import DeviceMatrix, DeviceVector, get_context
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 34
