@@ -107,3 +107,125 @@ def test_gmres_amg_solution_and_counts(gpu_ctx, dim, N):
     res = np.linalg.norm(sys_.b - sys_.A @ g["x"]) / np.linalg.norm(sys_.b)
     assert res <= 2e-10
     assert rel(g["x"], xd) <= 1e-8
+
+
+INEXACT_CG_OPTIONS = """
+-global_ksp_type fgmres
+-s_ksp_type cg
+-s_ksp_norm_type unpreconditioned
+-s_ksp_atol 0.0
+-s_ksp_rtol 1e-1
+-s_pc_type hypre
+-fp_ksp_type preonly
+-fp_pc_fieldsplit_type schur
+-fp_pc_fieldsplit_schur_fact_type lower
+-fp_pc_fieldsplit_schur_precondition selfp
+-fp_pc_fieldsplit_order fp
+-fp_fieldsplit_0_ksp_type cg
+-fp_fieldsplit_0_ksp_norm_type unpreconditioned
+-fp_fieldsplit_0_ksp_rtol 1e-2
+-fp_fieldsplit_0_ksp_atol 0.0
+-fp_fieldsplit_0_pc_type hypre
+-fp_fieldsplit_1_ksp_type cg
+-fp_fieldsplit_1_ksp_rtol 1e-2
+-fp_fieldsplit_1_ksp_atol 0.0
+-fp_fieldsplit_1_ksp_max_it 10
+-fp_fieldsplit_1_pc_type hypre
+"""
+
+
+@pytest.mark.parametrize("dim,N", [(2, 16), (3, 5)])
+def test_fgmres_inner_cg_amg_matches_oracle(gpu_ctx, dim, N):
+    """petsc-options-inexact style: inner CG + AMG to loose tolerances (a NONLINEAR preconditioner), outer FGMRES.
+    Exercises the device CG (fused SpMV+dot, device-resident alpha), all three PETSc norm types' default, and FGMRES."""
+    from oracle.amg import SAAMG, rigid_body_modes
+    from oracle.blockpc import BlockPC, SchurLower, krylov_solver
+    from oracle.krylov import gmres
+    from oracle.problems import swelling
+    sys_, par = swelling(dim, N, "diagonal")
+    par = dict(par)
+    par.update({"solver rtol": 1e-9, "solver atol": 0.0, "solver maxiter": 100, "solver type": "fgmres"})
+    B = rigid_body_modes(sys_.coords_s, dim)
+    amg_v = lambda M: SAAMG(M, dim, B)
+    amg_p = lambda M: SAAMG(M, 1, None)
+    k_s = krylov_solver("cg", amg_v, rtol=1e-1, atol=0.0, norm_type="unpreconditioned")
+    k_f = krylov_solver("cg", amg_v, rtol=1e-2, atol=0.0, norm_type="unpreconditioned")
+    k_p = krylov_solver("cg", amg_p, rtol=1e-2, atol=0.0, max_it=10)
+    pc = BlockPC(sys_, {"s": k_s, "fp": lambda M: SchurLower(M, sys_.nf, sys_.np_, k_f, k_p, "f")})
+    ro = gmres(lambda v: sys_.A @ v, sys_.b, pc, rtol=1e-9, atol=0.0, dtol=1e20, max_it=100, restart=100, flexible=True)
+    g = gpu_solve(sys_, par, INEXACT_CG_OPTIONS)
+    assert g["reason"] == 2
+    assert abs(g["its"] - ro.its) <= max(1, int(round(0.1 * ro.its)))
+    # flexible GMRES monitors the true residual even though the preconditioner is nonlinear
+    res = np.linalg.norm(sys_.b - sys_.A @ g["x"]) / np.linalg.norm(sys_.b)
+    assert res <= 2e-9
+    st = g["stats"]
+    # inner iteration counts per application agree with the oracle's within 20 %
+    for key, k in (("s", pc.k_s), ("fp_split0", pc.k_fp.k0), ("fp_split1", pc.k_fp.k1)):
+        gpu_avg = st["its_" + key] / max(st["calls_" + key], 1)
+        cpu_avg = k.total_its / max(k.calls, 1)
+        assert abs(gpu_avg - cpu_avg) <= 0.2 * cpu_avg + 0.5, (key, gpu_avg, cpu_avg)
+
+
+AMG_3WAY_OPTIONS = AMG_OPTIONS + """
+-f_ksp_type preonly
+-f_pc_type hypre
+-p_ksp_type preonly
+-p_pc_type hypre
+-diff_ksp_type preonly
+-diff_pc_type hypre
+"""
+
+
+def test_gmres_amg_three_way_matches_oracle(gpu_ctx):
+    """'diagonal 3-way' with one V-cycle per inner solve (prefixes s_ f_ p_ diff_): counts within 10 % of the oracle."""
+    from oracle.amg import SAAMG, rigid_body_modes
+    from oracle.blockpc import BlockPC, krylov_solver
+    from oracle.krylov import gmres
+    from oracle.problems import swelling
+    sys_, par = swelling(2, 12, "diagonal 3-way")
+    par = dict(par)
+    par.update({"solver rtol": 1e-9, "solver atol": 0.0, "solver maxiter": 200})
+    B = rigid_body_modes(sys_.coords_s, 2)
+    v = krylov_solver("preonly", lambda M: SAAMG(M, 2, B))
+    p = krylov_solver("preonly", lambda M: SAAMG(M, 1, None))
+    pc = BlockPC(sys_, {"s": v, "f": v, "p": p, "diff": p})
+    ro = gmres(lambda w: sys_.A @ w, sys_.b, pc, rtol=1e-9, atol=0.0, dtol=1e20, max_it=200, restart=200, pc_side="right")
+    g = gpu_solve(sys_, par, AMG_3WAY_OPTIONS)
+    assert g["reason"] == 2
+    assert abs(g["its"] - ro.its) <= max(1, int(round(0.1 * ro.its)))
+    assert np.linalg.norm(sys_.b - sys_.A @ g["x"]) <= 2e-9 * np.linalg.norm(sys_.b)
+
+
+def test_large_mesh_properties(gpu_ctx):
+    """Size-independent properties on a mesh too large for the oracle's direct solves (3D N=20, 424 k DoFs):
+    linearity of the device operator (BSR + diagonal-BSR + CSR split) against scipy, true residual of the
+    solve, monotone residual history, and linearity of the whole solve in b (linear preconditioner)."""
+    from oracle.problems import swelling
+    from poro_b200.lib.backend import DeviceVector
+    sys_, par = swelling(3, 20, "diagonal")
+    par = dict(par)
+    par.update({"solver rtol": 1e-8, "solver atol": 0.0, "solver maxiter": 100})
+    g = gpu_solve(sys_, par, AMG_OPTIONS, return_objects=True)
+    ksp = g["solver"].solver
+    assert ksp.reason == 2
+    x = g["x"]
+    nb = np.linalg.norm(sys_.b)
+    assert np.linalg.norm(sys_.b - sys_.A @ x) <= 1.5e-8 * nb
+    hist = np.array(ksp.getConvergenceHistory())
+    assert np.all(np.diff(hist) <= 1e-12 * hist[0])                  # GMRES residuals never increase
+    # operator linearity through the solver's internal product
+    rng = np.random.default_rng(5)
+    u, v = rng.standard_normal(sys_.n), rng.standard_normal(sys_.n)
+    du, dv, dw = DeviceVector(u, ctx=gpu_ctx), DeviceVector(v, ctx=gpu_ctx), DeviceVector(2.0 * u - 3.0 * v, ctx=gpu_ctx)
+    yu, yv, yw = (DeviceVector(n=sys_.n, ctx=gpu_ctx) for _ in range(3))
+    ksp.mult(du, yu); ksp.mult(dv, yv); ksp.mult(dw, yw)
+    gpu_ctx.sync()
+    assert rel(yu.numpy(), sys_.A @ u) <= 1e-13
+    assert rel(yw.numpy(), 2.0 * yu.numpy() - 3.0 * yv.numpy()) <= 1e-13
+    # the solve is linear in b: same iteration count, doubled solution
+    db2, dx2 = DeviceVector(2.0 * sys_.b, ctx=gpu_ctx), DeviceVector(n=sys_.n, ctx=gpu_ctx)
+    its1 = ksp.its
+    ksp.solve(db2, dx2)
+    assert ksp.its == its1
+    assert rel(dx2.numpy(), 2.0 * x) <= 1e-7
