@@ -57,13 +57,14 @@ def _worker(rank, world, port, N, pc_type, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("N,pc_type", [(3, "diagonal"), (4, "diagonal 3-way")])
-def test_slab_partition_world2(N, pc_type):
+@pytest.mark.parametrize("N,pc_type,world", [(3, "diagonal", 2), (4, "diagonal 3-way", 2), (4, "diagonal", 3)])
+def test_slab_partition_gloo(N, pc_type, world):
+    """world 3: the middle rank has two neighbours (the layout every rank but the ends has at 4 and 8 GPUs)."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000) + N
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, N, pc_type, q)) for r in range(2)]
+    port = 29500 + (os.getpid() % 2000) + N + 10 * world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, N, pc_type, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]
