@@ -229,3 +229,38 @@ def test_large_mesh_properties(gpu_ctx):
     ksp.solve(db2, dx2)
     assert ksp.its == its1
     assert rel(dx2.numpy(), 2.0 * x) <= 1e-7
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_inner_anderson_acceleration_matches_oracle(gpu_ctx, order):
+    """`inner accel order` > 0: AndersonAcceleration.get_next_vector on the preconditioner output
+    (lib/Preconditioner.py:248-249, lib/AndersonAcceleration.py:19-78).  The accelerated PC is stateful and
+    nonlinear, so only the first applications are compared one by one: PreconditionerCC.apply on a fixed sequence
+    of inputs must reproduce the oracle's sequence."""
+    from oracle.aar import AndersonAcceleration
+    from oracle.blockpc import BlockPC, exact_solvers
+    from oracle.problems import swelling
+    from poro_b200.lib.backend import DeviceVector
+    sys_, par = swelling(2, 6, "diagonal")
+    g = gpu_solve(sys_, par, EXACT_OPTIONS, overrides={"inner accel order": order, "solver maxiter": 1}, return_objects=True)
+    pcx = g["pc"].pc.getPythonContext()
+    # the 1-iteration solve above already consumed PC applications; replay the same sequence on the oracle:
+    # GMRES(right) with maxiter 1 applies the PC to v0 = b/||b|| and then to the update V y
+    pco = BlockPC(sys_, exact_solvers(), anderson=AndersonAcceleration(order))
+    v0 = sys_.b / np.linalg.norm(sys_.b)
+    z0 = pco(v0)
+    w = sys_.A @ z0
+    h = v0 @ w
+    w = w - h * v0
+    hn = np.linalg.norm(w)
+    den = np.hypot(h, hn)
+    y0 = (h / den) * np.linalg.norm(sys_.b) / den
+    pco(y0 * v0)
+    rng = np.random.default_rng(11)
+    for k in range(4):
+        x = rng.standard_normal(sys_.n)
+        dx, dy = DeviceVector(x, ctx=gpu_ctx), DeviceVector(n=sys_.n, ctx=gpu_ctx)
+        pcx.apply(None, dx, dy)
+        gpu_ctx.sync()
+        yo = pco(x)
+        assert rel(dy.numpy(), yo) <= 1e-6, (k, rel(dy.numpy(), yo))
