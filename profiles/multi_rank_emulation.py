@@ -1,5 +1,5 @@
 """CPU emulation (oracle AMG) of the multi-rank preconditioner variants: rank-local coarse levels, global coarsest
-solve, overlapping (RAS) local hierarchies, pressure Schur complement from owned parts.  python profiles/multi_rank_emulation.py N R"""
+solve, overlapping (RAS) local hierarchies, pressure Schur complement from owned parts.  python profiles/multi_rank_emulation.py N R   (N >= 10 so that every slab has at least two AMG levels)"""
 import sys, time, numpy as np, scipy.sparse as sp
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle.problems import swelling
