@@ -546,8 +546,41 @@ class PoroAssembler:
         b[bc] = 0.0
         return b
 
+    def rhs_vector_load_2d(self, side: str, g, field_off: int = 0):
+        """b for a VECTOR surface load on one side of a 2D mesh, g(x) -> (n, 2), interpolated linearly between the
+        facet's end vertices (a dolfin `Expression(..., degree=1)`, footing.py:38-39).  Returns the full-length vector.
+        Exact edge integrals of P1 x P2: int l_a phi_a = L/6, int l_a phi_b = 0, int l_a phi_mid = L/3."""
+        assert self.dim == 2
+        d = 2
+        ns = self.n2 * d
+        b = np.zeros(2 * ns + self.n1)
+        C, O = self.boundary_facets()
+        cells, X = self.mesh.cells, self.mesh.coords
+        edges = local_edges(2)
+        ax = "xy".index(side[0])
+        val = 0.0 if side[1] == "0" else self.mesh.length
+        for o in range(3):
+            sel = C[O == o]
+            loc = [i for i in range(3) if i != o]
+            fx = X[cells[sel][:, loc]]
+            on = np.all(np.abs(fx[:, :, ax] - val) < 1e-10 * max(self.mesh.length, 1.0), axis=1)
+            sel, fx = sel[on], fx[on]
+            if not len(sel):
+                continue
+            L = np.linalg.norm(fx[:, 1] - fx[:, 0], axis=1)
+            ga, gb = g(fx[:, 0]), g(fx[:, 1])                                   # (nfac, 2)
+            eloc = d + 1 + edges.index((min(loc), max(loc)))
+            da, db, dm = self.cell_p2[sel, loc[0]], self.cell_p2[sel, loc[1]], self.cell_p2[sel, eloc]
+            for comp in range(2):
+                np.add.at(b, field_off + da * d + comp, L * ga[:, comp] / 6.0)
+                np.add.at(b, field_off + db * d + comp, L * gb[:, comp] / 6.0)
+                np.add.at(b, field_off + dm * d + comp, L * (ga[:, comp] + gb[:, comp]) / 3.0)
+        bc = np.concatenate([self.bc_s.ravel(), self.bc_f.ravel(), np.zeros(self.n1, bool)])
+        b[bc] = 0.0
+        return b
+
     # -------- everything
-    def system(self, pc_type: str, t: float, neumann_solid=(), neumann_fluid=(), fs_sur=None, ff_sur=None) -> PoroSystem:
+    def system(self, pc_type: str, t: float, neumann_solid=(), neumann_fluid=(), fs_sur=None, ff_sur=None, b=None) -> PoroSystem:
         d = self.dim
         ns = nf = self.n2 * d
         npp = self.n1
@@ -555,7 +588,8 @@ class PoroAssembler:
         A = self.compose(self.field_blocks("A"))
         P = self.compose(self.field_blocks("P", pc_type))
         P_diff = self.compose(self.field_blocks("P_diff", pc_type), apply_p_bc=True) if three_way else None
-        b = self.rhs(t, neumann_solid, neumann_fluid, fs_sur, ff_sur)
+        if b is None:
+            b = self.rhs(t, neumann_solid, neumann_fluid, fs_sur, ff_sur)
         is_s = np.arange(ns, dtype=np.int64)
         is_f = ns + np.arange(nf, dtype=np.int64)
         is_p = ns + nf + np.arange(npp, dtype=np.int64)

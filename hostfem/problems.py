@@ -8,6 +8,8 @@ from __future__ import annotations
 
 import math
 
+import numpy as np
+
 from .fem import PoroAssembler, unit_cube_mesh, unit_square_mesh
 
 _SOLVER_KEYS_2D = {
@@ -68,4 +70,45 @@ def swelling(dim: int, N: int = 10, pc_type: str | None = None, overrides: dict 
     t = par["t0"] + par["dt"]
     sys_ = asm.system(par["pc type"], t, **loads)
     sys_.meta.update(dict(problem="swelling-%dd" % dim, N=N))
+    return sys_, par
+
+
+def footing_params() -> dict:
+    """Material + solver parameters of footing.py:42-84."""
+    E, nu = 3e4, 0.2
+    p = {"mu_f": 1e-3, "rhof": 1e3, "rhos": 500, "phi0": 1e-3, "mu_s": E / (2 * (1 + nu)),
+         "lmbda": E * nu / ((1 + nu) * (1 - 2 * nu)), "ks": 1e6, "kf": 1e-7, "dt": 0.1, "t0": 0.0, "tf": 0.1,
+         "fe degree solid": 2, "fe degree fluid": 2, "fe degree pressure": 1, "betas": -0.5, "betaf": 0.0, "betap": 1.0}
+    p.update(_SOLVER_KEYS_2D)
+    p.update({"solver rtol": 1e-6, "solver atol": 1e-4, "solver maxiter": 500, "pc type": "undrained"})
+    return p
+
+
+def footing(N: int = 10, pc_type: str | None = None, overrides: dict | None = None):
+    """footing.py (BASELINE config 1), one time step.  Square of side 64, solid clamped at the bottom, fluid no-slip
+    under the foot (top, |x - 32| < 16), pressure BC on the rest of the boundary, vertical load (0, -1e4) under
+    |x - 32| < 16 on the top side, P1-interpolated (footing.py:36-39, 93-110).
+
+    Deviation (documented): the reference refines the top-middle cells twice with dolfin's Plaza `refine`
+    (lib/MeshCreation.py:53-104), which cannot be reproduced without dolfin; this generator uses the uniform
+    N x N 'right'-diagonal mesh, and marks Dirichlet dofs nodewise instead of facetwise."""
+    par = footing_params()
+    if overrides:
+        par.update(overrides)
+    if pc_type is not None:
+        par["pc type"] = pc_type
+    length = 64.0
+    mesh = unit_square_mesh(N, length)
+    asm = PoroAssembler(mesh, par)
+    tol = 1e-10 * length
+    on_boundary = lambda X: (np.abs(X[:, 0]) < tol) | (np.abs(X[:, 0] - length) < tol) | (np.abs(X[:, 1]) < tol) | (np.abs(X[:, 1] - length) < tol)
+    foot = lambda X: (np.abs(X[:, 1] - length) < tol) & (np.abs(X[:, 0] - length / 2) < length / 4)
+    foot_not = lambda X: on_boundary(X) & ~foot(X)
+    asm.set_bcs(bcs_s=[("y0", None)], bcs_f=[(foot, None)], bcs_p=[foot_not])          # footing.py:97-108
+    t = par["t0"] + par["dt"]
+    val = min(t, 1.0) * 1e5
+    load = lambda X: np.stack([np.zeros(len(X)), np.where(np.abs(X[:, 0] - length / 2) < length / 4, -val, 0.0)], 1)
+    b = asm.rhs_vector_load_2d("y1", load, field_off=0)                                  # Neumann solid = TOP (footing.py:22)
+    sys_ = asm.system(par["pc type"], t, b=b)
+    sys_.meta.update(dict(problem="footing", N=N))
     return sys_, par

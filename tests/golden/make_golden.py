@@ -20,10 +20,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle.aar import AAR                                   # noqa: E402
 from oracle.blockpc import BlockPC, exact_solvers           # noqa: E402
 from oracle.krylov import gmres                              # noqa: E402
-from oracle.problems import swelling                         # noqa: E402
+from oracle.problems import footing, swelling                # noqa: E402
 
 CASES = [("swelling2d_N4_diagonal", 2, 4, "diagonal"), ("swelling2d_N4_diagonal3way", 2, 4, "diagonal 3-way"),
-         ("swelling3d_N2_diagonal", 3, 2, "diagonal"), ("swelling2d_N6_undrained", 2, 6, "undrained")]
+         ("swelling3d_N2_diagonal", 3, 2, "diagonal"), ("swelling2d_N6_undrained", 2, 6, "undrained"),
+         ("footing_N8_undrained", 0, 8, "undrained")]            # dim 0 = footing.py (BASELINE config 1)
 
 
 def csr_pack(prefix, M, out):
@@ -35,14 +36,14 @@ def csr_pack(prefix, M, out):
 
 def main():
     for name, dim, N, pct in CASES:
-        s, par = swelling(dim, N, pct)
+        s, par = footing(N, pct) if dim == 0 else swelling(dim, N, pct)
         A = lambda v: s.A @ v
         r = gmres(A, s.b, BlockPC(s, exact_solvers()), rtol=par["solver rtol"], atol=par["solver atol"], dtol=1e20,
                   max_it=par["solver maxiter"], restart=par["solver maxiter"], pc_side="right")
         a = AAR(par["AAR order"], par["AAR p"], par["AAR omega"], par["AAR beta"], A, BlockPC(s, exact_solvers()),
                 atol=par["solver atol"], rtol=par["solver rtol"], maxiter=par["solver maxiter"])
         xa = a.solve(s.b)
-        out = dict(dim=dim, N=N, pc_type=pct, b=s.b, is_s=s.is_s, is_f=s.is_f, is_p=s.is_p,
+        out = dict(dim=s.dim, N=N, pc_type=pct, b=s.b, is_s=s.is_s, is_f=s.is_f, is_p=s.is_p,
                    bcs_sub_pressure=s.bcs_sub_pressure, coords_s=s.coords_s, coords_p=s.coords_p,
                    gmres_x=r.x, gmres_its=r.its, gmres_history=np.array(r.history), gmres_reason=r.reason,
                    aar_x=xa, aar_its=a.it, aar_history=np.array(a.history),

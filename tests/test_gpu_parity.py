@@ -264,3 +264,15 @@ def test_inner_anderson_acceleration_matches_oracle(gpu_ctx, order):
         gpu_ctx.sync()
         yo = pco(x)
         assert rel(dy.numpy(), yo) <= 1e-6, (k, rel(dy.numpy(), yo))
+
+
+def test_footing_undrained_matches_oracle(gpu_ctx):
+    """BASELINE config 1 (footing.py, pc type 'undrained', the block lower-triangular 2-way PC with a non-zero
+    fp<-s coupling): exact blocks, same iteration count and solution as the oracle."""
+    from oracle.problems import footing
+    sys_, par = footing(12)
+    xo, its_o, hist_o = _oracle_exact(sys_, par)
+    g = gpu_solve(sys_, par, EXACT_OPTIONS)
+    assert g["its"] == its_o and g["reason"] in (2, 3)
+    assert rel(g["x"], xo) <= 1e-6
+    assert g["pc"].pc.getPythonContext().block_info("fps")[2] > 0        # the coupling block is really there

@@ -94,3 +94,18 @@ def test_pc_variants_differ_where_expected():
     dd = s3.P_diff[p][:, p]
     assert len(s3.bcs_sub_pressure) > 0
     assert np.all(dd.diagonal()[s3.bcs_sub_pressure] == 1.0)
+
+
+def test_footing_problem():
+    """footing.py (BASELINE config 1) on the uniform mesh: load resultant, BC sets, undrained PC converges."""
+    from oracle.blockpc import BlockPC, exact_solvers
+    from oracle.krylov import gmres
+    from oracle.problems import footing
+    s, par = footing(10)
+    assert s.n == 1885 and s.pc_type == "undrained" and par["solver atol"] == 1e-4
+    # vertical load -1e4 over the foot (width 32), nothing horizontal
+    assert abs(s.b[1:s.ns:2].sum() + 32 * 1e4) < 1e-6 and abs(s.b[0:s.ns:2]).sum() == 0.0
+    assert abs(s.b[s.ns:]).sum() == 0.0
+    r = gmres(lambda v: s.A @ v, s.b, BlockPC(s, exact_solvers()), rtol=par["solver rtol"], atol=par["solver atol"], dtol=1e20,
+              max_it=par["solver maxiter"], restart=par["solver maxiter"], pc_side="right")
+    assert r.reason in (2, 3) and r.its == 26
