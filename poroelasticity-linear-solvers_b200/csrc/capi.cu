@@ -89,6 +89,7 @@ int poro_ctx_destroy(poro_ctx* h) {
     Ctx& c = h->c;
     cudaSetDevice(c.device);
     dist_finalize(c);
+    for (auto e : c.prof.ev) cudaEventDestroy(e);
     if (c.h_pin) cudaFreeHost(c.h_pin);
     if (c.d_scal) cudaFree(c.d_scal);
     if (c.stream) cudaStreamDestroy(c.stream);
@@ -312,12 +313,6 @@ int poro_fields_set_coords(poro_ctx* h, int dim, const double* coords_s, const d
 // ---------------------------------------------------------------------------------------------
 // block extraction helpers
 // ---------------------------------------------------------------------------------------------
-template <class F>
-__global__ void k_fill_map(int64_t n, int* out, F f) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = f(i);
-}
-
 // columns: list of (field) pieces in order; rows: contiguous permuted range [r0, r1)
 static std::unique_ptr<MatOp> extract_block(poro_ctx* h, const Csr& Mp, int64_t r0, int64_t r1, std::vector<int> col_fields) {
     Ctx& c = h->c;

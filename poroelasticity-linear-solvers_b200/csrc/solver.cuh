@@ -117,13 +117,6 @@ struct KSP {
     int converged(double rn, int it, double& rnorm0, double& ttol) const;
 };
 
-// a configured inner KSP used as a preconditioner
-struct PCKsp : PC {
-    std::unique_ptr<KSP> ksp;
-    void apply(const double* x, double* y) override { ksp->solve(x, y); }
-    const char* kind() const override { return "ksp"; }
-};
-
 // PCFIELDSPLIT(schur) on the fp block (lib/Preconditioner.py:102-118, petsc-options-inexact:78-80)
 struct PCSchur : PC {
     Ctx* ctx = nullptr;

@@ -87,3 +87,13 @@ def test_preconditioner_rejects_unknown_pc_type():
            "inner maxiter": 1, "inner accel order": 0, "inner monitor": False}
     with pytest.raises(SystemExit):
         Preconditioner(None, None, None, None, par, [])
+
+
+def test_shipped_option_files_parse_and_match_bench():
+    from poro_b200.lib.Parser import parse_petsc_options
+    import bench
+    for name in ("petsc-options-exact", "petsc-options-inexact", "petsc-options-b200"):
+        opts = parse_petsc_options(open(os.path.join(ROOT, "options", name)).read())
+        assert len(opts) >= 10 and all(k.startswith("-") for k, _ in opts)
+    shipped = dict(parse_petsc_options(open(os.path.join(ROOT, "options", "petsc-options-b200")).read()))
+    assert shipped == dict(parse_petsc_options(bench.BENCH_OPTIONS))
