@@ -276,3 +276,27 @@ def test_footing_undrained_matches_oracle(gpu_ctx):
     assert g["its"] == its_o and g["reason"] in (2, 3)
     assert rel(g["x"], xo) <= 1e-6
     assert g["pc"].pc.getPythonContext().block_info("fps")[2] > 0        # the coupling block is really there
+
+
+def test_reference_split_order_inexact_file(gpu_ctx):
+    """options/petsc-options-inexact: the REFERENCE's fieldsplit order (split 0 = pressure, split 1 = fluid velocity
+    with the selfp Schur complement S_f solved exactly, lib/Preconditioner.py:113-114, petsc-options-inexact:78-106),
+    inner CG + AMG, outer FGMRES.  Same algorithm in the oracle: iteration counts within 10 %."""
+    import os
+    from oracle.amg import SAAMG, rigid_body_modes
+    from oracle.blockpc import LU, BlockPC, SchurLower, krylov_solver
+    from oracle.krylov import gmres
+    from oracle.problems import swelling
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys_, par = swelling(2, 10, "diagonal")
+    par = dict(par)
+    par.update({"solver rtol": 1e-8, "solver atol": 0.0, "solver maxiter": 200, "solver type": "fgmres"})
+    B = rigid_body_modes(sys_.coords_s, 2)
+    k_s = krylov_solver("cg", lambda M: SAAMG(M, 2, B), rtol=1e-1, atol=0.0, norm_type="unpreconditioned")
+    k_p = krylov_solver("cg", lambda M: SAAMG(M, 1, None), rtol=1e-4, atol=0.0, max_it=10)
+    pc = BlockPC(sys_, {"s": k_s, "fp": lambda M: SchurLower(M, sys_.nf, sys_.np_, k_p, lambda S: LU(S), "p")})
+    ro = gmres(lambda v: sys_.A @ v, sys_.b, pc, rtol=1e-8, atol=0.0, dtol=1e20, max_it=200, restart=200, flexible=True)
+    g = gpu_solve(sys_, par, open(os.path.join(root, "options", "petsc-options-inexact")).read())
+    assert g["reason"] == 2
+    assert abs(g["its"] - ro.its) <= max(1, int(round(0.1 * ro.its)))
+    assert np.linalg.norm(sys_.b - sys_.A @ g["x"]) <= 2e-8 * np.linalg.norm(sys_.b)
