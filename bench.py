@@ -34,6 +34,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("PORO_LOG_STDERR", "1")      # stdout carries only the JSON line
 
 BENCH_OPTIONS = """
 -global_ksp_type gmres
