@@ -300,3 +300,31 @@ def test_reference_split_order_inexact_file(gpu_ctx):
     assert g["reason"] == 2
     assert abs(g["its"] - ro.its) <= max(1, int(round(0.1 * ro.its)))
     assert np.linalg.norm(sys_.b - sys_.A @ g["x"]) <= 2e-8 * np.linalg.norm(sys_.b)
+
+
+def test_gmres_left_preconditioning_default(gpu_ctx):
+    """No `-global_ksp_pc_side`: PETSc's default LEFT preconditioning, which monitors ||M^-1 r|| (what the reference
+    runs when no option file is given)."""
+    from oracle.blockpc import BlockPC, exact_solvers
+    from oracle.krylov import gmres
+    from oracle.problems import swelling
+    sys_, par = swelling(2, 10, "diagonal")
+    left = EXACT_OPTIONS.replace("-global_ksp_pc_side right\n", "")
+    pc = BlockPC(sys_, exact_solvers())
+    ro = gmres(lambda v: sys_.A @ v, sys_.b, pc, rtol=par["solver rtol"], atol=par["solver atol"], dtol=1e20,
+               max_it=par["solver maxiter"], restart=par["solver maxiter"], pc_side="left")
+    g = gpu_solve(sys_, par, left)
+    assert g["its"] == ro.its
+    np.testing.assert_allclose(g["history"], ro.history, rtol=1e-6, atol=1e-14)
+    assert abs(g["history"][0] - np.linalg.norm(pc(sys_.b))) <= 1e-9 * g["history"][0]    # preconditioned norm
+    assert rel(g["x"], ro.x) <= 1e-8
+
+
+def test_cgs2_refinement_option(gpu_ctx):
+    """-global_ksp_gmres_cgs_refinement_type refine_always (CGS2): same iteration count, same solution."""
+    from oracle.problems import swelling
+    sys_, par = swelling(2, 10, "diagonal 3-way")
+    a = gpu_solve(sys_, par, EXACT_OPTIONS)
+    b = gpu_solve(sys_, par, EXACT_OPTIONS + "\n-global_ksp_gmres_cgs_refinement_type refine_always\n")
+    assert a["its"] == b["its"]
+    assert rel(a["x"], b["x"]) <= 1e-9
