@@ -21,4 +21,6 @@ blockpc    PreconditionerCC.apply 2-way / 3-way (lib/Preconditioner.py:141-250)
 aar        AAR.solve incl. its quirks (lib/AAR.py:46-137)
 anderson   AndersonAcceleration.get_next_vector (lib/AndersonAcceleration.py:19-78)
 amg        CPU restatement of OUR smoothed-aggregation AMG (not hypre)
+ddamg      CPU twin of the row-partitioned (multi-GPU) preconditioners: rank-local hierarchies, global smoothing
+fastmat    OpenMP CSR matvec for the timed CPU baseline (oracle/csrc/omp_kernels.c)
 """

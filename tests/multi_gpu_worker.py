@@ -54,7 +54,10 @@ dist.all_reduce(num)
 err = float(torch.sqrt(num[0] / num[1]))
 if rank == 0:
     print("ranks", world, "N", N, "its", ksp.its, "reason", ksp.reason, "spmv err %.2e" % err_spmv, "solution err %.2e" % err, flush=True)
-ok = err_spmv < 1e-13 and ksp.reason == 2 and err < 1e-8
+# iteration counts of the CPU twin of the row-partitioned preconditioner (oracle/ddamg.py, tests/test_oracle_ddamg.py)
+TWIN_ITS = {(8, 2): 49, (8, 4): 70}
+twin_ok = (N, world) not in TWIN_ITS or abs(ksp.its - TWIN_ITS[(N, world)]) <= max(2, TWIN_ITS[(N, world)] // 10)
+ok = err_spmv < 1e-13 and ksp.reason == 2 and err < 1e-8 and twin_ok
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0 and int(flag) == 1:
