@@ -94,7 +94,7 @@ def localize_columns(M_rows: sp.csr_matrix, owned_global: np.ndarray, halo_globa
     sg = allg[order]
     pos = np.searchsorted(sg, M_rows.indices)
     assert np.all(sg[pos] == M_rows.indices), "matrix references a column that is neither owned nor in the halo"
-    out = sp.csr_matrix((M_rows.data, order[pos].astype(np.int32), M_rows.indptr), shape=(n_owned, n_owned + n_halo))
+    out = sp.csr_matrix((M_rows.data, order[pos].astype(np.int32), M_rows.indptr), shape=(M_rows.shape[0], n_owned + n_halo))
     out.sort_indices()
     return out
 
@@ -115,6 +115,9 @@ class LocalSystem:
     owned_global: np.ndarray
     plan: HaloPlan
     meta: dict = field(default_factory=dict)
+    # optional (overlap_rows=True): P with the rows of the halo dofs appended, (n_owned + n_halo) square, columns outside
+    # [owned | halo] dropped -- the input a halo-aware Schur complement / overlapping hierarchy needs (round-2 plan)
+    P_ext: sp.csr_matrix | None = None
 
 
 @dataclass
@@ -143,7 +146,17 @@ def _gather_fn(world):
     return g
 
 
-def distributed_problem(dim: int, N: int, pc_type: str, rank: int, world: int, ctx=None, overrides=None) -> DistributedProblem:
+def restrict_rows_to_columns(M_rows: sp.csr_matrix, keep_global: np.ndarray, n_cols_global: int) -> sp.csr_matrix:
+    """Drop the entries of M_rows whose (global) column is not in keep_global."""
+    mask = np.zeros(n_cols_global, bool)
+    mask[keep_global] = True
+    C = M_rows.tocoo()
+    sel = mask[C.col]
+    return sp.csr_matrix((C.data[sel], (C.row[sel], C.col[sel])), shape=M_rows.shape)
+
+
+def distributed_problem(dim: int, N: int, pc_type: str, rank: int, world: int, ctx=None, overrides=None,
+                        overlap_rows: bool = False) -> DistributedProblem:
     """Assemble this rank's z-slab of the 3D swelling problem and install the halo plan on `ctx`."""
     assert dim == 3, "slab partition is implemented for the structured cube"
     from hostfem.fem import PoroAssembler, unit_cube_mesh    # host assembler (stands in for FEniCS; not the oracle)
@@ -156,6 +169,8 @@ def distributed_problem(dim: int, N: int, pc_type: str, rank: int, world: int, c
     a, b_ = slab_ranges(L, world)[rank]
     k0 = max(0, (a - 1) // 2 if a > 0 else 0)
     k1 = min(N, (b_ - 1) // 2 + 1)
+    if overlap_rows:            # one more cell layer: the rows of the halo dofs become complete as well
+        k0, k1 = max(0, k0 - 1), min(N, k1 + 1)
     mesh = unit_cube_mesh(N, 1e-2, k_range=(k0, k1))
     asm = PoroAssembler(mesh, par)
     asm.set_bcs(bcs_s=[("x0", 0), ("y0", 1), ("z0", 2)], bcs_f=[("z0", None), ("z1", None)],
@@ -178,7 +193,8 @@ def distributed_problem(dim: int, N: int, pc_type: str, rank: int, world: int, c
 
     t = par["t0"] + par["dt"]
     A = asm.compose(asm.field_blocks("A"))[owned_global]
-    P = asm.compose(asm.field_blocks("P", pc_type))[owned_global]
+    P_full = asm.compose(asm.field_blocks("P", pc_type))
+    P = P_full[owned_global]
     three_way = "3-way" in pc_type
     Pd = asm.compose(asm.field_blocks("P_diff", pc_type), apply_p_bc=True)[owned_global] if three_way else None
     bfull = asm.rhs(t, ["x1", "y1", "z1"], ["x0", "y0"], _traction(0.9), _traction(0.1))
@@ -200,6 +216,10 @@ def distributed_problem(dim: int, N: int, pc_type: str, rank: int, world: int, c
     bc_p_local = np.flatnonzero(asm.bc_p[own1]).astype(np.int64)
     sys_ = LocalSystem(3, A_l, P_l, Pd_l, bfull[owned_global], is_s, is_f, is_p, bc_p_local, coords_s, coords_p,
                        owned_global, plan, dict(N=N, planes=(a, b_), cells=(k0, k1)))
+    if overlap_rows:
+        halo_rows = restrict_rows_to_columns(P_full[plan.halo_global], ext_global, ns + nf + n1)
+        halo_l = localize_columns(halo_rows, owned_global, plan.halo_global)
+        sys_.P_ext = sp.vstack([P_l, halo_l], format="csr")
     if ctx is not None:
         if world > 1:
             import torch

@@ -10,7 +10,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, N, pc_type, q):
+def _worker(rank, world, port, N, pc_type, q, overlap=True):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch
@@ -19,7 +19,7 @@ def _worker(rank, world, port, N, pc_type, q):
     try:
         from oracle.problems import swelling
         from poro_b200.partition import distributed_problem
-        prob = distributed_problem(3, N, pc_type, rank, world, ctx=None)
+        prob = distributed_problem(3, N, pc_type, rank, world, ctx=None, overlap_rows=overlap)
         s, plan = prob.sys, prob.sys.plan
         glob, _ = swelling(3, N, pc_type)
         x = np.random.default_rng(7).standard_normal(glob.n)
@@ -42,6 +42,14 @@ def _worker(rank, world, port, N, pc_type, q):
             got = Ml @ xe
             assert np.linalg.norm(got - ref) <= 1e-12 * np.linalg.norm(ref)
         assert np.allclose(s.b, glob.b[s.owned_global], rtol=1e-12, atol=1e-18)
+        # overlap rows: the rows of the halo dofs, restricted to [owned | halo] columns, equal the global ones
+        if overlap:
+            ext_g = np.concatenate([s.owned_global, plan.halo_global])
+            ref_ext = glob.P[ext_g][:, ext_g]
+            assert s.P_ext.shape == ref_ext.shape
+            assert abs(s.P_ext - ref_ext).max() <= 1e-12 * abs(ref_ext).max()
+        else:
+            assert s.P_ext is None
         n_own = torch.tensor([len(s.owned_global)])
         dist.all_reduce(n_own)
         assert int(n_own) == glob.n == prob.n_global
@@ -57,14 +65,14 @@ def _worker(rank, world, port, N, pc_type, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("N,pc_type,world", [(3, "diagonal", 2), (4, "diagonal 3-way", 2), (4, "diagonal", 3)])
-def test_slab_partition_gloo(N, pc_type, world):
+@pytest.mark.parametrize("N,pc_type,world,overlap", [(3, "diagonal", 2, False), (4, "diagonal 3-way", 2, True), (4, "diagonal", 3, True)])
+def test_slab_partition_gloo(N, pc_type, world, overlap):
     """world 3: the middle rank has two neighbours (the layout every rank but the ends has at 4 and 8 GPUs)."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + (os.getpid() % 2000) + N + 10 * world
-    procs = [ctx.Process(target=_worker, args=(r, world, port, N, pc_type, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, N, pc_type, q, overlap)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]
