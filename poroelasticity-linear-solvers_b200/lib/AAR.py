@@ -29,6 +29,7 @@ class AAR:
                                                  float(omega), float(beta), float(atol), float(rtol), int(maxiter),
                                                  int(bool(monitor_convergence)), C.byref(h)))
         self.h = h
+        self._keep = (matA, pc)   # borrowed by the library, see include/poro.h
         self.it = 0
 
     def set_up(self):

@@ -26,6 +26,7 @@ class _KSP:
         _capi.check(ctx.lib.poro_ksp_create(ctx.h, A.mat().handle, pc.handle, ksp_type.encode(), float(rtol), float(atol),
                                             float(divtol), int(maxit), int(restart), prefix.encode(), C.byref(h)))
         self.h = h
+        self._keep = (A, pc)      # the library borrows A when the numbering is already field-major: keep it alive
         self.its, self.reason, self.rnorm = 0, 0, 0.0
         self.max_it = maxit
 
