@@ -130,6 +130,12 @@ def oracle_solver(sys_, par, max_it, threaded=True):
         A = fastmat.OmpCsr(A)
 
     def run():
+        if threaded:
+            # the OpenMP team of the matvec and numpy's BLAS pool would fight for the cores: BLAS gets one thread
+            from threadpoolctl import threadpool_limits
+            with threadpool_limits(limits=1, user_api="blas"):
+                return gmres(lambda v: A @ v, sys_.b, pc, rtol=RTOL, atol=0.0, dtol=1e20, max_it=max_it,
+                             restart=max(max_it, 1), pc_side="right")
         return gmres(lambda v: A @ v, sys_.b, pc, rtol=RTOL, atol=0.0, dtol=1e20, max_it=max_it, restart=max(max_it, 1),
                      pc_side="right")
     return run

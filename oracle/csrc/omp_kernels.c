@@ -8,7 +8,8 @@ int oracle_omp_threads(void) { return omp_get_max_threads(); }
 
 void oracle_csr_matvec(int64_t nrows, const int64_t* indptr, const int32_t* indices, const double* data,
                        const double* x, double* y) {
-#pragma omp parallel for schedule(static, 256)
+    /* small (coarse-level) matrices are not worth a fork/join */
+#pragma omp parallel for schedule(static, 256) if (indptr[nrows] > 200000)
     for (int64_t i = 0; i < nrows; ++i) {
         double s = 0.0;
         for (int64_t k = indptr[i]; k < indptr[i + 1]; ++k) s += data[k] * x[indices[k]];
