@@ -111,11 +111,15 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def oracle_solver(sys_, par, max_it, threaded=True):
-    """The CPU port of the benchmarked algorithm (same options as BENCH_OPTIONS)."""
+def oracle_solver(sys_, par, max_it):
+    """The CPU port of the benchmarked algorithm (same options as BENCH_OPTIONS).
+
+    Returns {label: (run, cores)}: the numpy/scipy oracle on one thread, and the same preconditioner handed
+    to the C + OpenMP solve loop (oracle/csrc/cpu_solver.c) with the thread count that is fastest on this host."""
     from oracle.amg import SAAMG, rigid_body_modes
     from oracle.blockpc import BlockPC, SchurLower, krylov_solver
     from oracle.krylov import gmres
+    from oracle import cport
     dim = sys_.dim
     B = rigid_body_modes(sys_.coords_s, dim)
     amg_s = lambda M: SAAMG(M, dim, B, theta=0.04)                              # -s_pc_amg_theta 0.04
@@ -124,33 +128,44 @@ def oracle_solver(sys_, par, max_it, threaded=True):
     mkfp = lambda M: SchurLower(M, sys_.nf, sys_.np_, krylov_solver("preonly", cheb_f), krylov_solver("preonly", amg_p), "f")
     pc = BlockPC(sys_, {"s": krylov_solver("preonly", amg_s), "fp": mkfp})
     A = sys_.A
-    if threaded:
-        from oracle import fastmat
-        fastmat.accelerate(pc)          # every `M @ x` of the timed loop -> OpenMP CSR kernel (oracle/csrc/omp_kernels.c)
-        A = fastmat.OmpCsr(A)
 
-    def run():
-        if threaded:
-            # the OpenMP team of the matvec and numpy's BLAS pool would fight for the cores: BLAS gets one thread
-            from threadpoolctl import threadpool_limits
-            with threadpool_limits(limits=1, user_api="blas"):
-                return gmres(lambda v: A @ v, sys_.b, pc, rtol=RTOL, atol=0.0, dtol=1e20, max_it=max_it,
-                             restart=max(max_it, 1), pc_side="right")
+    def run_numpy():
         return gmres(lambda v: A @ v, sys_.b, pc, rtol=RTOL, atol=0.0, dtol=1e20, max_it=max_it, restart=max(max_it, 1),
                      pc_side="right")
-    return run
+
+    cs = cport.CSolver(sys_, pc)
+    # thread count: hosts differ (shared vCPUs make a full OpenMP team slower than two threads), so probe
+    # a few team sizes on a 4-iteration solve and keep the fastest
+    tmax = cport.threads()
+    best_t, best_dt = 1, None
+    for t in sorted({1, 2, 4, 8, 16, 32, 64, tmax}):
+        if t > tmax:
+            continue
+        cport.set_threads(t)
+        cs.solve(sys_.b, RTOL, 0.0, 2)
+        t0 = time.perf_counter()
+        cs.solve(sys_.b, RTOL, 0.0, 4)
+        dt = time.perf_counter() - t0
+        if best_dt is None or dt < best_dt:
+            best_t, best_dt = t, dt
+        if dt > 4 * best_dt:
+            break
+    cport.set_threads(best_t)
+
+    def run_c():
+        return cs.solve(sys_.b, RTOL, 0.0, max_it)
+
+    return {"numpy/scipy, 1 thread": (run_numpy, 1), "C + OpenMP solve loop on %d threads" % best_t: (run_c, best_t)}
 
 
 def cpu_baseline(sample_n: int, budget_s: float = 20.0):
     """Oracle port timed on the host cores on a bounded sample: the same problem on a smaller
-    mesh (the metric is normalised per DoF x iteration).  Both the plain scipy build (1 thread) and the
-    OpenMP-matvec build (all host threads) are timed; the faster one is reported with its thread count."""
-    from oracle import fastmat
+    mesh (the metric is normalised per DoF x iteration).  Both builds of the port are timed (numpy/scipy on one
+    thread, C + OpenMP on the fastest team size); the faster one is reported with its thread count."""
     from oracle.problems import swelling
     sys_, par = swelling(3, sample_n, "diagonal")
     best = None
-    for threaded in (False, True):
-        run = oracle_solver(sys_, par, 100, threaded=threaded)
+    for label, (run, cores) in oracle_solver(sys_, par, 100).items():
         dt, r = None, None
         for _ in range(2):
             t0 = time.perf_counter()
@@ -159,20 +174,13 @@ def cpu_baseline(sample_n: int, budget_s: float = 20.0):
             dt = d if dt is None else min(dt, d)
             if d > budget_s / 4:
                 break
-        cores = fastmat.threads() if threaded else 1
         cand = {"value": sys_.n * r.its / dt, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": "same problem on mesh N=%d (%d DoFs), full solve to rtol 1e-8: %d its in %.2f s; %s; NOT PETSc/hypre"
-                          % (sample_n, sys_.n, r.its, dt, "numpy + OpenMP CSR matvec on %d threads" % cores if threaded
-                             else "numpy/scipy, 1 thread"),
+                          % (sample_n, sys_.n, r.its, dt, label),
                 "its": r.its, "seconds": dt}
         if best is None or cand["value"] > best["value"]:
             best = cand
     return best
-
-
-def _threads():
-    from oracle import fastmat
-    return fastmat.threads()
 
 
 def run_reference(args):
@@ -182,14 +190,13 @@ def run_reference(args):
     from oracle.problems import swelling
     sample_n = args.cpu_sample_n
     sys_, par = swelling(3, sample_n, "diagonal")
-    # pick the faster of the two CPU builds (scipy single thread / OpenMP matvec on all host threads)
-    from oracle import fastmat
+    # pick the faster of the two CPU builds of the port
     cand = []
-    for threaded in (False, True):
-        rr = oracle_solver(sys_, par, 100, threaded=threaded)
-        t0 = time.perf_counter(); rr(); cand.append((time.perf_counter() - t0, threaded, rr))
-    _, threaded, run = min(cand, key=lambda c: c[0])
-    ncores = fastmat.threads() if threaded else 1
+    for label, (rr, cores) in oracle_solver(sys_, par, 100).items():
+        t0 = time.perf_counter(); rr(); cand.append((time.perf_counter() - t0, label, rr, cores))
+    _, label, run, ncores = min(cand, key=lambda c: c[0])
+    for _ in range(args.warmup):
+        run()
     t0 = time.perf_counter()
     its = 0
     for _ in range(args.steps):
@@ -203,7 +210,7 @@ def run_reference(args):
                                    "on a bounded sample mesh N=%d (%d DoFs)" % (sample_n, sys_.n)},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "port",
                              "sample": "mesh N=%d (%d DoFs), %d full solves, %s; NOT PETSc/hypre" % (
-                                 sample_n, sys_.n, args.steps, "numpy + OpenMP CSR matvec" if threaded else "numpy/scipy 1 thread")},
+                                 sample_n, sys_.n, args.steps, label)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -216,7 +223,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--mesh-n", type=int, default=34, help="cells per side at 1 GPU (swelling-3d.py -N)")
-    ap.add_argument("--cpu-sample-n", type=int, default=12)
+    ap.add_argument("--cpu-sample-n", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

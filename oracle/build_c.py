@@ -1,18 +1,24 @@
-"""Builds the oracle's optional OpenMP kernels (CPU baseline only) into oracle/_omp_kernels.so."""
+"""Builds the oracle's C parts (CPU baseline only): the OpenMP CSR matvec (oracle/_omp_kernels.so) and the
+C + OpenMP solve loop (oracle/_cpu_solver.so)."""
 import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "csrc", "omp_kernels.c")
-OUT = os.path.join(HERE, "_omp_kernels.so")
+TARGETS = [("omp_kernels.c", "_omp_kernels.so"), ("cpu_solver.c", "_cpu_solver.so")]
+OUT = os.path.join(HERE, TARGETS[0][1])
 
 
 def build(force=False):
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= os.path.getmtime(SRC):
-        return OUT
-    subprocess.run(["gcc", "-O3", "-march=x86-64-v2", "-fopenmp", "-shared", "-fPIC", SRC, "-o", OUT], check=True)
-    return OUT
+    outs = []
+    for src, out in TARGETS:
+        src, out = os.path.join(HERE, "csrc", src), os.path.join(HERE, out)
+        if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+            subprocess.run(["gcc", "-O3", "-march=x86-64-v2", "-fopenmp", "-shared", "-fPIC", src, "-o", out, "-lm"],
+                           check=True)
+        outs.append(out)
+    return outs[0]
 
 
 if __name__ == "__main__":
-    print(build(force=True))
+    build(force=True)
+    print([t[1] for t in TARGETS])

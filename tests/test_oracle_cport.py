@@ -1,0 +1,58 @@
+"""The C + OpenMP solve loop of the CPU baseline (oracle/csrc/cpu_solver.c) against the numpy oracle:
+same iteration count, same residual history, same solution."""
+import numpy as np
+import pytest
+
+from oracle import cport
+from oracle.amg import SAAMG, rigid_body_modes
+from oracle.blockpc import BlockPC, SchurLower, krylov_solver
+from oracle.krylov import gmres
+from oracle.problems import swelling
+
+
+def _pc(sys_, first="f"):
+    B = rigid_body_modes(sys_.coords_s, sys_.dim)
+    amg_s = lambda M: SAAMG(M, sys_.dim, B, theta=0.04)
+    cheb_f = lambda M: SAAMG(M, sys_.dim, B, max_levels=1, cheby_degree=4)
+    amg_p = lambda M: SAAMG(M, 1, None)
+    mkfp = lambda M: SchurLower(M, sys_.nf, sys_.np_, krylov_solver("preonly", cheb_f), krylov_solver("preonly", amg_p), first)
+    return BlockPC(sys_, {"s": krylov_solver("preonly", amg_s), "fp": mkfp})
+
+
+# the undrained case (non-zero fp<-s coupling in P) stagnates with these inner solvers, so it is compared after
+# a fixed 25 iterations (reason -3 on both sides)
+@pytest.mark.parametrize("dim,n,pc_type,max_it", [(3, 4, "diagonal", 200), (2, 12, "diagonal", 200), (3, 3, "undrained", 25)])
+def test_c_solve_matches_numpy(dim, n, pc_type, max_it):
+    sys_, _ = swelling(dim, n, pc_type)
+    pc = _pc(sys_)
+    ref = gmres(lambda v: sys_.A @ v, sys_.b, pc, rtol=1e-8, atol=0.0, dtol=1e20, max_it=max_it, restart=max_it, pc_side="right")
+    for t in (1, 3):
+        cport.set_threads(t)
+        got = cport.CSolver(sys_, pc).solve(sys_.b, 1e-8, 0.0, max_it)
+        # summation orders differ (blocked dots, thread teams): long solves drift in the last digits of the
+        # late residuals, so the history is compared over its first 30 entries and the count to +-1
+        assert abs(got.its - ref.its) <= 1 and got.reason == ref.reason
+        k = min(30, got.its, ref.its)
+        np.testing.assert_allclose(got.history[:k], ref.history[:k], rtol=1e-6)
+        np.testing.assert_allclose(got.x, ref.x, rtol=0, atol=1e-7 * np.abs(ref.x).max())
+
+
+def test_c_vcycle_matches_numpy():
+    sys_, _ = swelling(3, 4, "diagonal")
+    pc = _pc(sys_)
+    amg = pc.k_s.M
+    assert len(amg.levels) >= 2
+    b = np.random.default_rng(0).standard_normal(amg.levels[0].A.shape[0])
+    np.testing.assert_allclose(cport.CAmg(amg)(b), amg(b), rtol=1e-12, atol=1e-14 * np.abs(amg(b)).max())
+
+
+def test_c_port_rejects_other_configurations():
+    sys_, _ = swelling(2, 6, "diagonal")
+    with pytest.raises(ValueError):
+        cport.CSolver(sys_, _pc(sys_, first="p"))
+
+
+def test_c_port_iteration_limit():
+    sys_, _ = swelling(2, 8, "diagonal")
+    got = cport.CSolver(sys_, _pc(sys_)).solve(sys_.b, 1e-14, 0.0, 3)
+    assert got.its == 3 and got.reason == -3
