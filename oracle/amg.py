@@ -171,8 +171,13 @@ class Level:
 class SAAMG:
     def __init__(self, A: sp.csr_matrix, bs: int = 1, B: np.ndarray | None = None, theta: float = 0.08,
                  max_levels: int = 10, coarse_size: int = 400, cheby_degree: int = 2, cheby_ratio: float = 10.0,
-                 power_its: int = 15, dense_limit: int = 4096):
+                 power_its: int = 15, dense_limit: int = 4096, node_labels: np.ndarray | None = None):
+        """node_labels (one int per node): aggregates never cross a label boundary ("uncoupled" aggregation
+        of a row-partitioned matrix: each rank aggregates its own nodes) while smoothing of P and the Galerkin
+        product stay global.  The coarse nodes inherit the label of their aggregate."""
         A = sp.csr_matrix(A)
+        labels = None if node_labels is None else np.asarray(node_labels)
+        self.level_labels = []
         n = A.shape[0]
         if B is None:
             B = np.zeros((n, bs))
@@ -197,6 +202,11 @@ class SAAMG:
             dir_rows = (rowabs - np.abs(d)) <= 1e-14 * np.abs(d)
             B[dir_rows] = 0.0
             S = strength_graph(A, bs, theta)
+            if labels is not None:
+                G = S.tocoo()
+                keep = labels[G.row] == labels[G.col]
+                S = sp.coo_matrix((G.data[keep], (G.row[keep], G.col[keep])), shape=S.shape).tocsr()
+                S.sort_indices()
             agg, n_agg = aggregate_mis2(S)
             if n_agg == 0 or n_agg * B.shape[1] >= 0.8 * n:
                 break
@@ -210,7 +220,15 @@ class SAAMG:
                 Ac = (Ac + sp.diags(dead.astype(float))).tocsr()
             L.P, L.R = P, P.T.tocsr()
             L.agg, L.n_agg = agg, n_agg
+            if labels is not None:
+                self.level_labels.append(labels)
+                mem = agg >= 0
+                cl = np.zeros(n_agg, labels.dtype)
+                cl[agg[mem]] = labels[mem]
+                labels = cl
             A, B, bs = Ac, Bc, B.shape[1]
+        if labels is not None:
+            self.level_labels.append(labels)
         Lc = self.levels[-1]
         # coarsest level: dense inverse when small (amg.cu: poro_amg_dense_limit), else smoothing only
         self.coarse_direct = Lc.A.shape[0] <= dense_limit

@@ -80,7 +80,17 @@ s_local = lambda M: DDAmg(M, 3, Bl, ps, **KW_S)
 s_single = lambda M: SAAMG(M, 3, Bg, **KW_S)
 s_ras = lambda layers: (lambda M: RASAmg(M, 3, Bg, ps, ext_parts(plane_s, layers), **KW_S))
 
+# "uncoupled" aggregation: aggregates never cross a rank boundary (each rank aggregates its own nodes with the
+# existing kernels), prolongator smoothing and the Galerkin product use the distributed operator
+lab_s_dof = np.zeros(s.ns, int); lab_p = np.zeros(s.np_, int)
+for r_, (p0, p1) in enumerate(zip(ps, pp)):
+    lab_s_dof[p0] = r_; lab_p[p1] = r_
+s_uncoupled = lambda B: (lambda M: SAAMG(M, 3, B, node_labels=lab_s_dof[::3], **KW_S))
+p_uncoupled = lambda S: SAAMG(glob_S(S), 1, None, node_labels=lab_p)
+
 solve("single hierarchy everywhere (1 GPU)", s_single, cheb_f, p_single)
+solve("uncoupled aggregation + distributed Galerkin (s, S_p)", s_uncoupled(Bg), cheb_f, p_uncoupled)
+solve("  same, rigid-body modes about each rank's own centre", s_uncoupled(Bl), cheb_f, p_uncoupled)
 solve("round 1: s local coarse, S_p from owned parts + local AMG", s_local, cheb_f, p_local)
 solve("s local coarse, S_p halo-aware + global level-0 smoothing", s_local, cheb_f, p_globalS_localAmg)
 solve("s single hierarchy, S_p from owned parts + local AMG", s_single, cheb_f, p_local)
