@@ -453,7 +453,8 @@ class PoroAssembler:
         for fi, fr in enumerate("sfp"):
             row_blocks = []
             for fc in "sfp":
-                m = self._to_csr(*blocks[fr + fc])
+                v = blocks[fr + fc]                     # (kind, pattern data), or an already global sparse block
+                m = self._to_csr(*v) if isinstance(v, tuple) else self._to_csr(v)
                 bc = bcrow[fr]
                 if bc.any():
                     keep = np.repeat(~bc, np.diff(m.indptr))
