@@ -75,26 +75,20 @@ class StructuredGenerator:
 
     set_bcs = PoroAssembler.set_bcs
 
-    # ---- one field block --------------------------------------------------------------------------------
-    def expand(self, K: np.ndarray, kr: int, kc: int, br: int, bc: int, plane_range=None):
-        """Global block from the macro-cell matrix K ((nloc_r^d * br) x (nloc_c^d * bc), dense).
-        Returns a BSR matrix with blocks br x bc; with plane_range=(a, b) only the rows of the nodes on the
-        planes a <= x_last < b of the ROW lattice are generated (global row and column numbering kept)."""
+    # ---- class stencils ---------------------------------------------------------------------------------
+    def class_stencils(self, K: np.ndarray, kr: int, kc: int, br: int, bc: int):
+        """Yields (axis class codes, axis classes, column offsets (tuples), value blocks) for every position class
+        of the row lattice: the stencil of the class = sum over the cells containing the node of the macro-cell rows."""
         d, N = self.dim, self.N
-        Lr, Lc = self.L[kr], self.L[kc]
         nr, nc = self.nloc[kr], self.nloc[kc]
         sc = 2 if kc == 2 else 1
-        n_rows = Lr ** d
-        per_class = []
-        counts = np.zeros(n_rows, np.int64)
-        tables = []
-        for combo in itertools.product(_axis_classes(kr, N), repeat=d):
-            # ---- the stencil of this class: column offset (relative to sc * c0) -> value block
+        classes = _axis_classes(kr, N)
+        for codes in itertools.product(range(len(classes)), repeat=d):
+            combo = tuple(classes[c] for c in codes)
             st = {}
             for cells in itertools.product(*[c[1] for c in combo]):           # the cells containing the node
                 a_loc = sum(cells[m][1] * nr ** m for m in range(d))
-                for b in itertools.product(range(nc), repeat=d):              # their column nodes
-                    b = b[::-1]                                               # b[m] = local coordinate on axis m
+                for b in itertools.product(range(nc), repeat=d):              # their column nodes; b[m] = local coordinate
                     b_loc = sum(b[m] * nc ** m for m in range(d))
                     blk = K[a_loc * br:(a_loc + 1) * br, b_loc * bc:(b_loc + 1) * bc]
                     if not blk.any():
@@ -110,6 +104,40 @@ class StructuredGenerator:
                     del st[t]
             deltas = sorted(st, key=lambda t: t[::-1])                        # ascending column id: last axis slowest
             vals = np.array([st[t] for t in deltas]).reshape(len(deltas), br, bc)
+            yield codes, combo, deltas, vals
+
+    def table_arrays(self, K: np.ndarray, kr: int, kc: int, br: int, bc: int):
+        """The class tables in the layout of csrc/next/gen_stencil.cuh (BlockTable): class id = sum code_m * ncl^m
+        with ncl = 4 (P2 rows) or 3 (P1 rows); (cls_ptr int32, off int64 column-node offsets, vals)."""
+        d = self.dim
+        ncl = 4 if kr == 2 else 3
+        Lc = self.L[kc]
+        per = {}
+        for codes, combo, deltas, vals in self.class_stencils(K, kr, kc, br, bc):
+            cid = sum(codes[m] * ncl ** m for m in range(d))
+            per[cid] = (np.array([sum(t[m] * Lc ** m for m in range(d)) for t in deltas], np.int64), vals)
+        cls_ptr = np.zeros(ncl ** d + 1, np.int32)
+        offs, vs = [], []
+        for c in range(ncl ** d):
+            o, v = per.get(c, (np.zeros(0, np.int64), np.zeros((0, br, bc))))
+            cls_ptr[c + 1] = cls_ptr[c] + len(o)
+            offs.append(o); vs.append(v.reshape(len(o), br * bc))
+        return cls_ptr, np.concatenate(offs), np.ascontiguousarray(np.concatenate(vs))
+
+    # ---- one field block --------------------------------------------------------------------------------
+    def expand(self, K: np.ndarray, kr: int, kc: int, br: int, bc: int, plane_range=None):
+        """Global block from the macro-cell matrix K ((nloc_r^d * br) x (nloc_c^d * bc), dense).
+        Returns a BSR matrix with blocks br x bc; with plane_range=(a, b) only the rows of the nodes on the
+        planes a <= x_last < b of the ROW lattice are generated (global row and column numbering kept)."""
+        d, N = self.dim, self.N
+        Lr, Lc = self.L[kr], self.L[kc]
+        nr, nc = self.nloc[kr], self.nloc[kc]
+        sc = 2 if kc == 2 else 1
+        n_rows = Lr ** d
+        per_class = []
+        counts = np.zeros(n_rows, np.int64)
+        tables = []
+        for codes, combo, deltas, vals in self.class_stencils(K, kr, kc, br, bc):
             tables.append((combo, deltas, vals))
             if not deltas:
                 continue
