@@ -18,6 +18,15 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 
+def time_levels(t0: float, tf: float, dt: float):
+    """The time levels AbstractPhysics.solve visits (lib/AbstractPhysics.py:73-75: `while t < tf: t += dt`)."""
+    out, t = [], t0
+    while t < tf - 1e-12:
+        t += dt
+        out.append(t)
+    return out
+
+
 def run(problem: str, default_N: int, argv=None):
     from hostfem import problems
     from poro_b200.lib.backend import DeviceMatrix, DeviceVector, get_context
@@ -53,13 +62,17 @@ def run(problem: str, default_N: int, argv=None):
     pc = pcw.get_pc()
     solver = Solver(A, b, pc, par, index_map)
     solver.create_solver(A, b, pc)
-    # AbstractPhysics.solve: every shipped driver runs exactly one step (t0 = 0, tf = dt = 0.1); the right-hand
-    # side depends on t only through the tractions (lib/Assembler.py:267-268), so later steps re-use b's pattern
+    # AbstractPhysics.solve: every shipped driver runs exactly one step (t0 = 0, tf = dt = 0.1); with
+    # --time-final the loop continues: the right-hand side depends on t only through the loads
+    # (lib/Assembler.py:267-268), matrices, preconditioner and solver are those of the first step
     t, tf, dt = par["t0"], par.get("tf", par["dt"]), par["dt"]
     t0_sim = time()
     current = time()
-    while t < tf - 1e-12:
-        t += dt
+    b_host = sys_.b
+    for step, t in enumerate(time_levels(t, tf, dt)):
+        if step > 0:
+            b_host = sys_.meta["rhs_at"](t)
+            b = DeviceVector(b_host, ctx=ctx)
         solver.set_up()
         solver.solve(b.vec(), sol.vec())
         its = solver.getIterationNumber()
@@ -69,6 +82,6 @@ def run(problem: str, default_N: int, argv=None):
     pcw.print_timings()
     solver.print_timings()
     x = sol.numpy()
-    res = np.linalg.norm(sys_.b - sys_.A @ x) / max(np.linalg.norm(sys_.b), 1e-300)
+    res = np.linalg.norm(b_host - sys_.A @ x) / max(np.linalg.norm(b_host), 1e-300)
     parprint("true relative residual = {:.3e}".format(res))
     return dict(its=its, x=x, residual=res, n=sys_.n)

@@ -69,7 +69,8 @@ def swelling(dim: int, N: int = 10, pc_type: str | None = None, overrides: dict 
         par["pc type"] = pc_type
     t = par["t0"] + par["dt"]
     sys_ = asm.system(par["pc type"], t, **loads)
-    sys_.meta.update(dict(problem="swelling-%dd" % dim, N=N))
+    # the right-hand side of a later time step (lib/Assembler.py:267-268: only the tractions depend on t)
+    sys_.meta.update(dict(problem="swelling-%dd" % dim, N=N, rhs_at=lambda tt: asm.rhs(tt, **loads)))
     return sys_, par
 
 
@@ -106,9 +107,12 @@ def footing(N: int = 10, pc_type: str | None = None, overrides: dict | None = No
     foot_not = lambda X: on_boundary(X) & ~foot(X)
     asm.set_bcs(bcs_s=[("y0", None)], bcs_f=[(foot, None)], bcs_p=[foot_not])          # footing.py:97-108
     t = par["t0"] + par["dt"]
-    val = min(t, 1.0) * 1e5
-    load = lambda X: np.stack([np.zeros(len(X)), np.where(np.abs(X[:, 0] - length / 2) < length / 4, -val, 0.0)], 1)
-    b = asm.rhs_vector_load_2d("y1", load, field_off=0)                                  # Neumann solid = TOP (footing.py:22)
-    sys_ = asm.system(par["pc type"], t, b=b)
-    sys_.meta.update(dict(problem="footing", N=N))
+
+    def rhs_at(tt):
+        val = min(tt, 1.0) * 1e5
+        load = lambda X: np.stack([np.zeros(len(X)), np.where(np.abs(X[:, 0] - length / 2) < length / 4, -val, 0.0)], 1)
+        return asm.rhs_vector_load_2d("y1", load, field_off=0)                           # Neumann solid = TOP (footing.py:22)
+
+    sys_ = asm.system(par["pc type"], t, b=rhs_at(t))
+    sys_.meta.update(dict(problem="footing", N=N, rhs_at=rhs_at))
     return sys_, par

@@ -109,3 +109,25 @@ def test_footing_problem():
     r = gmres(lambda v: s.A @ v, s.b, BlockPC(s, exact_solvers()), rtol=par["solver rtol"], atol=par["solver atol"], dtol=1e20,
               max_it=par["solver maxiter"], restart=par["solver maxiter"], pc_side="right")
     assert r.reason in (2, 3) and r.its == 26
+
+
+def test_time_levels_and_rhs_of_later_steps():
+    """examples/_driver.py: the time levels of AbstractPhysics.solve and the right-hand side of a later step
+    (only the loads depend on t, lib/Assembler.py:267-268)."""
+    import importlib.util
+    import math
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("example_driver", os.path.join(root, "examples", "_driver.py"))
+    drv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(drv)
+    assert drv.time_levels(0.0, 0.1, 0.1) == [0.1]
+    assert np.allclose(drv.time_levels(0.0, 0.3, 0.1), [0.1, 0.2, 0.3])
+    from hostfem import problems
+    sys_, par = problems.swelling(2, 4, "diagonal")
+    rhs_at = sys_.meta["rhs_at"]
+    assert np.array_equal(rhs_at(par["t0"] + par["dt"]), sys_.b)
+    mag = lambda t: 1 - math.exp(-(t ** 2) / 0.25)
+    np.testing.assert_allclose(rhs_at(0.2), sys_.b * (mag(0.2) / mag(0.1)), rtol=1e-12, atol=0)
+    sysf, parf = problems.footing(4)
+    np.testing.assert_allclose(sysf.meta["rhs_at"](0.3), 3.0 * sysf.b, rtol=1e-12, atol=0)     # load = min(t, 1) * 1e5
