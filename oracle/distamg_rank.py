@@ -254,3 +254,15 @@ class RankAmg:
 
     def __call__(self, b_owned):
         return self._cycle(0, b_owned)
+
+
+def dist_selfp_schur(comm: Comm, plan0: Plan, A10_local: sp.csr_matrix, A01_rows_glob: sp.csr_matrix, d00_owned: np.ndarray,
+                     A11_rows_glob: sp.csr_matrix) -> sp.csr_matrix:
+    """Exact selfp Schur complement of the OWNED rows of split 1 (the pressure in the benchmark's split order):
+        S[owned, :] = A11[owned, :] - A10[owned, [owned0 | ghost0]] diag(A00)^-1 A01[[owned0 | ghost0], :]
+    A10_local has local columns [owned | ghost] of split 0 with halo plan `plan0`; the A01 rows and the diagonal of the
+    ghost dofs arrive by one sparse-row and one vector halo exchange.  Columns of the result are global ids of split 1.
+    Round 1 drops the ghost terms (capi.cu: S from owned parts only), which is part of its iteration growth."""
+    d_ext = halo_vec(comm, plan0, d00_owned)
+    A01_ext = sp.vstack([A01_rows_glob, halo_rows(comm, plan0, A01_rows_glob)]).tocsr()
+    return (sp.csr_matrix(A11_rows_glob) - A10_local @ sp.diags(1.0 / d_ext) @ A01_ext).tocsr()

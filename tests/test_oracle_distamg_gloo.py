@@ -48,6 +48,23 @@ def _worker(rank, world, port, N, kw, q):
         y = mine(rhs[a:b])
         y_ref = ref(rhs)[a:b]
         assert np.abs(y - y_ref).max() <= 1e-10 * np.abs(y_ref).max()
+        # exact selfp Schur complement of the owned pressure rows (S_p = A_pp - A_pf diag(A_ff)^-1 A_fp)
+        from oracle.distamg_rank import Plan, dist_selfp_schur, localize
+        Pm = sp.csr_matrix(sys_.P)
+        perm_f, off_f = _slab_perm(sys_.coords_s, N, world, 3)          # f lives on the same nodes as s
+        perm_p, off_p = _slab_perm(sys_.coords_p, N, world, 1)
+        Aff = Pm[sys_.is_f][:, sys_.is_f][perm_f][:, perm_f].tocsr()
+        Afp = Pm[sys_.is_f][:, sys_.is_p][perm_f][:, perm_p].tocsr()
+        Apf = Pm[sys_.is_p][:, sys_.is_f][perm_p][:, perm_f].tocsr()
+        App = Pm[sys_.is_p][:, sys_.is_p][perm_p][:, perm_p].tocsr()
+        fa, fb, pa, pb = int(off_f[rank]), int(off_f[rank + 1]), int(off_p[rank]), int(off_p[rank + 1])
+        Apf_loc, ghost_f = localize(Apf[pa:pb], fa, fb)
+        plan_f = Plan(comm, off_f, ghost_f)
+        S_rows = dist_selfp_schur(comm, plan_f, Apf_loc, Afp[fa:fb], Aff.diagonal()[fa:fb], App[pa:pb])
+        S_ref = (App - Apf @ sp.diags(1.0 / Aff.diagonal()) @ Afp).tocsr()[pa:pb]
+        assert abs(S_rows - S_ref).max() <= 1e-13 * abs(S_ref).max()
+        S_owned_only = (App[pa:pb] - Apf[pa:pb, fa:fb] @ sp.diags(1.0 / Aff.diagonal()[fa:fb]) @ Afp[fa:fb]).tocsr()
+        assert abs(S_owned_only - S_ref).max() > 1e-3 * abs(S_ref).max()      # what round 1 assembles is NOT the Schur complement
         q.put((rank, "ok", len(mine.levels), comm.messages))
     except Exception:                                        # pragma: no cover
         import traceback
