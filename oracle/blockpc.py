@@ -153,3 +153,49 @@ class SchurLower:
         y1 = self.k1(x1 - self.A10 @ y0)
         yf, yp = (y1, y0) if self.first == "p" else (y0, y1)
         return np.concatenate([yf, yp])
+
+
+class SchurLowerCC:
+    """2-split lower Schur fieldsplit on the fp block (velocity first) with an additive Cahouet-Chabard-type
+    preconditioner for the pressure Schur complement (round-2 candidate, profiles/r1_schur_cc_study.md):
+
+        y_f = K0(P_ff) \\ x_f ;  r = x_p - P_pf y_f ;  y_p = K_mass(S_mass) \\ r + K_visc(S_visc) \\ r
+        S_mass = P_pp - P_pf diag(d_mass)^-1 P_fp     (d_mass ~ diag of the mass + drag part of P_ff)
+        S_visc = w_visc * M_p                          (the viscous limit of the Schur complement)
+
+    `cc_from_matrices` derives d_mass and S_visc from the assembled A and P plus two scalars of the reference's
+    parameter dict, i.e. from what crosses the library boundary."""
+
+    def __init__(self, Mfp_fp, nf, npp, make_k0, make_kmass, make_kvisc, d_mass, S_visc):
+        f = np.arange(nf)
+        p = nf + np.arange(npp)
+        self.nf, self.np_ = nf, npp
+        self.A00 = submatrix(Mfp_fp, f, f)
+        self.A01 = submatrix(Mfp_fp, f, p)
+        self.A10 = submatrix(Mfp_fp, p, f)
+        self.A11 = submatrix(Mfp_fp, p, p)
+        self.S_mass = (self.A11 - self.A10 @ sp.diags(1.0 / d_mass) @ self.A01).tocsr()
+        self.S_visc = sp.csr_matrix(S_visc)
+        self.k0, self.k_mass, self.k_visc = make_k0(self.A00), make_kmass(self.S_mass), make_kvisc(self.S_visc)
+
+    def __call__(self, x):
+        y0 = self.k0(x[: self.nf])
+        r = x[self.nf:] - self.A10 @ y0
+        return np.concatenate([y0, self.k_mass(r) + self.k_visc(r)])
+
+
+def cc_from_matrices(sys_, par):
+    """(d_mass, S_visc) for SchurLowerCC from the assembled matrices and the physical parameters:
+        A_fs = -(phi^2 / (k_f dt)) M_v  (rows of fluid Dirichlet dofs zeroed)  ->  diag(c M_v) = c dt k_f / phi^2 |diag(A_fs)|
+        P_pp = (phi_s^2 / (k_s dt) + beta_p) M_p  (`diagonal` splitting)       ->  M_p
+    with c = rho_f phi / dt + (1 + beta_f) phi^2 / k_f and w_visc = phi d / (2 mu_f) (beta_CC1, lib/Assembler.py:131)."""
+    phi0, dt, kf, d = par["phi0"], par["dt"], par["kf"], sys_.dim
+    phis = 1.0 - phi0
+    drag = phi0 ** 2 / kf
+    c = par["rhof"] * phi0 / dt + (1.0 + par["betaf"]) * drag
+    Afs = submatrix(sys_.A, sys_.is_f, sys_.is_s)
+    dm = np.abs(Afs.diagonal()) * (c * dt / drag)
+    d_mass = np.where(dm > 0, dm, 1.0)
+    beta_p = par["betap"] * phis ** 2 / (dt * (2 * par["mu_s"] / d + par["lmbda"]))
+    Mp = submatrix(sys_.P, sys_.is_p, sys_.is_p) / (phis ** 2 / (par["ks"] * dt) + beta_p)
+    return d_mass, (phi0 * d / (2.0 * par["mu_f"])) * Mp

@@ -122,3 +122,33 @@ def test_anderson_acceleration_fixed_point():
     for _ in range(6):
         x = acc.get_next_vector(0.5 * x + c)
     assert np.linalg.norm(x - 2 * c) < 1e-10
+
+
+def test_cahouet_chabard_schur_is_mesh_independent_in_2d():
+    """Round-2 candidate (profiles/r1_schur_cc_study.md): with exact blocks the selfp pressure Schur complement makes
+    the 2-way variant mesh dependent in 2D, the additive Cahouet-Chabard form does not; its data comes from the
+    assembled matrices and two scalars of the parameter dict (cc_from_matrices)."""
+    from hostfem.problems import swelling_assembler
+    from oracle.blockpc import LU, SchurLower, SchurLowerCC, cc_from_matrices
+    its = {"selfp": [], "cc": []}
+    for N in (8, 16, 32):
+        asm, par, loads = swelling_assembler(2, N)
+        sys_ = asm.system("diagonal", par["t0"] + par["dt"], **loads)
+        d_mass, S_visc = cc_from_matrices(sys_, par)
+        # the same data straight from the assembler's building blocks
+        c = asm._coeffs()
+        cM = c["rhof"] * c["idt"] * c["phi0"] + (1.0 + c["betaf"]) * c["phi0"] ** 2 * c["ikf"]
+        ref_d = np.where(asm.bc_f.ravel(), 1.0, cM * asm._to_csr("22", asm._mass_blocks()).diagonal())
+        np.testing.assert_allclose(d_mass, ref_d, rtol=1e-10)
+        ref_S = (c["phi0"] * 2 / (2 * c["mu_f"])) * asm._to_csr("11", asm.Mp)
+        assert abs(S_visc - ref_S).max() <= 1e-10 * abs(ref_S).max()
+        lu = lambda M: LU(M)
+        for name, mkfp in (("selfp", lambda M: SchurLower(M, sys_.nf, sys_.np_, lu, lu, "f")),
+                           ("cc", lambda M: SchurLowerCC(M, sys_.nf, sys_.np_, lu, lu, lu, d_mass, S_visc))):
+            pc = BlockPC(sys_, {"s": lu, "fp": mkfp})
+            r = gmres(lambda v: sys_.A @ v, sys_.b, pc, rtol=1e-6, atol=1e-8, dtol=1e20, max_it=200, restart=200, pc_side="right")
+            assert r.reason > 0
+            its[name].append(r.its)
+    assert its["cc"][-1] <= its["cc"][0] + 4                 # flat
+    assert its["selfp"][-1] >= its["selfp"][0] + 8           # grows
+    assert its["cc"][-1] < its["selfp"][-1]
