@@ -22,5 +22,7 @@ aar        AAR.solve incl. its quirks (lib/AAR.py:46-137)
 anderson   AndersonAcceleration.get_next_vector (lib/AndersonAcceleration.py:19-78)
 amg        CPU restatement of OUR smoothed-aggregation AMG (not hypre)
 ddamg      CPU twin of the row-partitioned (multi-GPU) preconditioners: rank-local hierarchies, global smoothing
-fastmat    OpenMP CSR matvec for the timed CPU baseline (oracle/csrc/omp_kernels.c)
+distamg    rank-level restatement of the DISTRIBUTED hierarchy (uncoupled aggregation, distributed Galerkin), all ranks
+           emulated in one process; distamg_rank: the same as one rank over torch.distributed (gloo)
+cport      ctypes glue of csrc/cpu_solver.c: the timed solve loop of the CPU baseline in C + OpenMP
 """

@@ -1,10 +1,9 @@
-"""Builds the oracle's C parts (CPU baseline only): the OpenMP CSR matvec (oracle/_omp_kernels.so) and the
-C + OpenMP solve loop (oracle/_cpu_solver.so)."""
+"""Builds the oracle's C part (CPU baseline only): the C + OpenMP solve loop (oracle/_cpu_solver.so)."""
 import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-TARGETS = [("omp_kernels.c", "_omp_kernels.so"), ("cpu_solver.c", "_cpu_solver.so")]
+TARGETS = [("cpu_solver.c", "_cpu_solver.so")]
 OUT = os.path.join(HERE, TARGETS[0][1])
 
 
