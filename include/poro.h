@@ -9,7 +9,7 @@
  *  - every function returns 0 on success, <0 on error; poro_last_error() gives the message.
  *    Nothing throws across the ABI.  Non-convergence is NOT an error (PETSc semantics): read
  *    `reason` (PETSc KSPConvergedReason codes: 2 rtol, 3 atol, 4 its(preonly), -3 max_it,
- *    -4 dtol, -5 breakdown, -8 indefinite, -9 nan).
+ *    -4 dtol, -5 breakdown, -8 indefinite PC, -9 nan, -10 indefinite operator).
  *  - all arithmetic is fp64; column indices int32; row pointers int64 at the ABI.
  *  - pointers named *_dev are device pointers on the ctx's GPU (e.g. torch tensor
  *    data_ptr()); *_host are host pointers.  Vectors are caller-owned and borrowed for the
@@ -47,6 +47,9 @@ int poro_options_clear(poro_ctx* ctx);
 /* number of CUDA kernels this ctx has launched so far (bench.py's gpu_launches) */
 int64_t poro_launch_count(poro_ctx* ctx);
 int poro_sync(poro_ctx* ctx);
+/* CUDA-event stopwatch on the library's own stream (torch.cuda.Event would only see torch's current stream) */
+int poro_timer_start(poro_ctx* ctx);
+int poro_timer_stop(poro_ctx* ctx, double* elapsed_ms);
 
 /* ---- matrices ------------------------------------------------------------------------
  * A.mat(), P.mat(), P_diff.mat() handed to Solver / Preconditioner
@@ -106,6 +109,14 @@ int poro_ksp_solve(poro_ksp* ksp, const double* b_dev, double* x_dev, int* its, 
 /* same with HOST vectors: copies b in and x out inside the call (the end-to-end path) */
 int poro_ksp_solve_host(poro_ksp* ksp, const double* b_host, double* x_host, int* its, int* reason, double* rnorm);
 int poro_ksp_residual_history(poro_ksp* ksp, double* out, int cap, int* n);
+/* KSP.setInitialGuessNonzero -- commented out at lib/Solver.py:94; the time loop (lib/AbstractPhysics.py:73-81,
+ * lib/Poromechanics.py:70-98) re-solves with the same operators every step, so the previous step's solution in x is a
+ * useful start.  Also `-<prefix>ksp_initial_guess_nonzero`.  Convergence is then measured against ||b|| (PETSc default). */
+int poro_ksp_set_initial_guess_nonzero(poro_ksp* ksp, int flag);
+/* per-field infinity norms (abs_s, abs_f, abs_p per iteration) of the true residual recorded by the
+ * `-<prefix>ksp_monitor_fields` monitor / `-<prefix>ksp_convergence_test_fields` test: the `converged` callback the
+ * reference defines at lib/Solver.py:8-51 and never installs.  `-<prefix>ksp_converged_reason` prints PETSc's line. */
+int poro_ksp_field_history(poro_ksp* ksp, double* out, int cap, int* n);
 int poro_ksp_destroy(poro_ksp* ksp);
 
 /* ---- AAR ------------------------------------------------------------------------------
@@ -125,6 +136,9 @@ int poro_pc_block_info(poro_pc* pc, const char* name, int64_t* nrows, int64_t* n
 int poro_pc_block_copy(poro_pc* pc, const char* name, int64_t* rowptr, int32_t* col, double* val);
 /* one application of the inner solver of a block: "s","f","p","fp","diff" (z = K \ r) */
 int poro_pc_inner_solve(poro_pc* pc, const char* name, const double* r_dev, double* z_dev);
+/* iterations / reason / residual norm of the last application of an inner solver ("s","f","p","fp","diff","fp0","fp1"):
+ * what `ksp.getIterationNumber()` reports in the single-block drivers (solid.py:177-180, fluid-pressure.py:133-136) */
+int poro_pc_inner_result(poro_pc* pc, const char* name, int* its, int* reason, double* rnorm);
 /* AMG hierarchy of a block's inner PC: per level rows and nnz; returns number of levels */
 int poro_pc_amg_info(poro_pc* pc, const char* name, int64_t* rows, int64_t* nnz, int cap, int* nlevels);
 /* live profile of the outer operator product (the dominant SpMV): CUDA events recorded on the

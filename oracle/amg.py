@@ -171,7 +171,8 @@ class Level:
 class SAAMG:
     def __init__(self, A: sp.csr_matrix, bs: int = 1, B: np.ndarray | None = None, theta: float = 0.08,
                  max_levels: int = 10, coarse_size: int = 400, cheby_degree: int = 2, cheby_ratio: float = 10.0,
-                 power_its: int = 15, dense_limit: int = 4096, node_labels: np.ndarray | None = None):
+                 power_its: int = 15, dense_limit: int = 4096, node_labels: np.ndarray | None = None,
+                 local_smoothing: bool = False):
         """node_labels (one int per node): aggregates never cross a label boundary ("uncoupled" aggregation
         of a row-partitioned matrix: each rank aggregates its own nodes) while smoothing of P and the Galerkin
         product stay global.  The coarse nodes inherit the label of their aggregate."""
@@ -212,7 +213,19 @@ class SAAMG:
                 break
             T, Bc = tentative_prolongator(agg, n_agg, bs, B)
             omega = 4.0 / (3.0 * L.lmax / 1.1)
-            P = (T - sp.diags(omega * L.dinv) @ (A @ T)).tocsr()
+            if labels is not None and local_smoothing:
+                # block-diagonal prolongator (csrc/amg.cu, distributed set-up): rows of the nodes that touch another
+                # rank (either direction of the pattern) keep their tentative row, every other row sees only owned
+                # columns anyway -> P never leaves its rank; the Galerkin product still uses the full operator
+                C = A.tocoo()
+                cross = labels[C.row // bs] != labels[C.col // bs]
+                bnd = np.zeros(n // bs, bool)
+                bnd[C.row[cross] // bs] = True
+                bnd[C.col[cross] // bs] = True
+                keep_row = np.repeat(~bnd, bs).astype(float)
+                P = (T - sp.diags(omega * L.dinv * keep_row) @ (A @ T)).tocsr()
+            else:
+                P = (T - sp.diags(omega * L.dinv) @ (A @ T)).tocsr()
             Ac = (P.T @ A @ P).tocsr()
             dc = Ac.diagonal()
             dead = dc == 0

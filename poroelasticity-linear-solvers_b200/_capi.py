@@ -29,6 +29,8 @@ SIGNATURES = {
     "poro_options_set": [vp, C.c_char_p, C.c_char_p],
     "poro_options_clear": [vp],
     "poro_sync": [vp],
+    "poro_timer_start": [vp],
+    "poro_timer_stop": [vp, c_f64p],
     "poro_mat_create_csr": [vp, C.c_int64, C.c_int64, vp, vp, vp, C.c_int, C.POINTER(vp)],
     "poro_mat_destroy": [vp],
     "poro_mat_info": [vp, c_i64p, c_i64p, c_i64p],
@@ -46,6 +48,9 @@ SIGNATURES = {
     "poro_ksp_solve": [vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int), c_f64p],
     "poro_ksp_solve_host": [vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int), c_f64p],
     "poro_ksp_residual_history": [vp, c_f64p, C.c_int, C.POINTER(C.c_int)],
+    "poro_ksp_set_initial_guess_nonzero": [vp, C.c_int],
+    "poro_ksp_field_history": [vp, c_f64p, C.c_int, C.POINTER(C.c_int)],
+    "poro_pc_inner_result": [vp, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), c_f64p],
     "poro_ksp_destroy": [vp],
     "poro_aar_create": [vp, vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                         C.POINTER(vp)],
@@ -153,6 +158,15 @@ class Context:
 
     def sync(self):
         check(self.lib.poro_sync(self.h))
+
+    def timer_start(self):
+        check(self.lib.poro_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        """Milliseconds between timer_start and now, measured by CUDA events on the library's stream."""
+        ms = C.c_double()
+        check(self.lib.poro_timer_stop(self.h, C.byref(ms)))
+        return ms.value
 
     def init_dist(self, rank: int, nranks: int, unique_id: bytes):
         check(self.lib.poro_ctx_init_dist(self.h, rank, nranks, unique_id))

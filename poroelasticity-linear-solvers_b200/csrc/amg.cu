@@ -10,6 +10,8 @@
 // Apply: V-cycle with Chebyshev smoothing on D^-1 A (fused SpMV + update kernel), dense
 // inverse on the coarsest level.
 #include "amg.cuh"
+#include "dist.cuh"
+#include "distamg.cuh"
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <chrono>
@@ -336,10 +338,34 @@ struct Tick {
     }
 };
 
+// distributed power iteration: start vector hashed from GLOBAL ids, halo exchange before every product, all-reduced norms
+static double power_lmax_dist(Ctx& c, const Csr& A, DistPlan& plan, const double* dinv, int its) {
+    const int n = plan.n_owned, ng = plan.n_ghost;
+    DBuf<double> v((size_t)n + ng), w((size_t)n);
+    {
+        double* vv = v.p; const uint32_t off = (uint32_t)plan.offset;
+        pfor(c, n, [=] __device__(int64_t i) { vv[i] = (double)(hash32(off + (uint32_t)i) % 2048u) / 1024.0 - 1.0; });
+    }
+    double nv = norm2_host(c, v.p, n);
+    if (nv == 0) return 1.0;
+    vec_scale(c, v.p, 1.0 / nv, n);
+    double lam = 1.0;
+    for (int it = 0; it < its; ++it) {
+        dist_halo_vec(c, plan, v.p, 1, v.p + n);
+        spmv(c, A, v.p, w.p);
+        vec_pmult(c, w.p, dinv, w.p, n);
+        lam = norm2_host(c, w.p, n);
+        if (lam == 0.0) return 1.0;
+        vec_waxpby(c, v.p, 1.0 / lam, w.p, 0.0, w.p, n);
+    }
+    return lam;
+}
+
 // ---- set-up ---------------------------------------------------------------------------------
-void Amg::setup(Ctx& c, const Csr& A, int bs, const double* B_dev, int k, const AmgParams& p) {
-    // the hierarchy is built on this rank's owned block: its reductions must not be collective
-    struct LocalScope { Ctx& c; bool old; LocalScope(Ctx& c_) : c(c_), old(c_.local_only) { c.local_only = true; } ~LocalScope() { c.local_only = old; } } local_scope(c);
+void Amg::setup(Ctx& c, const Csr& A, int bs, const double* B_dev, int k, const AmgParams& p, DistPlan* plan0) {
+    dist = plan0 != nullptr && c.nranks > 1;
+    // a hierarchy without a plan is built on this rank's owned block: its reductions must not be collective
+    struct LocalScope { Ctx& c; bool old; LocalScope(Ctx& c_, bool loc) : c(c_), old(c_.local_only) { if (loc) c.local_only = true; } ~LocalScope() { c.local_only = old; } } local_scope(c, !dist);
     ctx = &c;
     par = p;
     A0 = &A;
@@ -357,19 +383,35 @@ void Amg::setup(Ctx& c, const Csr& A, int bs, const double* B_dev, int k, const 
     }
     Csr Anext;
     bool have_next = false;
+    std::unique_ptr<DistPlan> next_plan;
+    const bool verbose = c.has_opt("-poro_verbose");
     while (true) {
         auto L = std::make_unique<AmgLevel>();
         if (have_next) L->A = std::move(Anext);
         AmgLevel* Lp = L.get();
         const Csr* Acur = levels.empty() ? &A : &Lp->A;
+        if (dist) {
+            if (levels.empty()) Lp->plan = plan0;
+            else { Lp->owned_plan = std::move(next_plan); Lp->plan = Lp->owned_plan.get(); }
+            PORO_REQUIRE(Acur->ncols == Lp->plan->n_owned + Lp->plan->n_ghost && Acur->nrows == Lp->plan->n_owned,
+                         "distributed level operator and its halo plan disagree");
+        }
         levels.push_back(std::move(L));
         Lp->bs = bs;
         n = Acur->nrows;
+        const int n_gh = dist ? Lp->plan->n_ghost : 0;
+        const int64_t n_glob = dist ? Lp->plan->offsets.back() : n;
         make_dinv(c, *Acur, Lp->dinv);
-        { Tick t(c, "power iteration"); Lp->lmax = 1.1 * power_lmax(c, *Acur, Lp->dinv.p, par.power_its); }
-        if (c.has_opt("-poro_verbose")) fprintf(stderr, "    [amg] level %d: n=%d nnz=%lld bs=%d lmax=%.4f\n", (int)levels.size() - 1, n, (long long)Acur->nnz, bs, Lp->lmax);
-        Lp->x.alloc(n); Lp->b.alloc(n); Lp->r.alloc(n); Lp->d0.alloc(n); Lp->d1.alloc(n);
-        if (n <= par.coarse_size || (int)levels.size() >= par.max_levels) break;
+        {
+            Tick t(c, "power iteration");
+            Lp->lmax = 1.1 * (dist ? power_lmax_dist(c, *Acur, *Lp->plan, Lp->dinv.p, par.power_its) : power_lmax(c, *Acur, Lp->dinv.p, par.power_its));
+        }
+        if (verbose && c.rank == 0)
+            fprintf(stderr, "    [amg] level %d: n=%d (global %lld) nnz=%lld bs=%d lmax=%.4f%s\n", (int)levels.size() - 1, n, (long long)n_glob,
+                    (long long)Acur->nnz, bs, Lp->lmax, dist ? " distributed" : "");
+        Lp->x.alloc((size_t)n + n_gh); Lp->b.alloc(n); Lp->r.alloc((size_t)n + n_gh); Lp->d0.alloc((size_t)n + n_gh); Lp->d1.alloc((size_t)n + n_gh);
+        if (dist) Lp->ext.alloc((size_t)n + n_gh);
+        if (n_glob <= par.coarse_size || (int)levels.size() >= par.max_levels) break;
         // Dirichlet rows (diagonal only) carry no near-nullspace
         {
             const int* rp = Acur->rowptr.p; const int* cc = Acur->col.p; const double* v = Acur->val.p;
@@ -380,34 +422,65 @@ void Amg::setup(Ctx& c, const Csr& A, int bs, const double* B_dev, int k, const 
                 if (off <= 1e-14 * fabs(d)) for (int j = 0; j < kk; ++j) b[(size_t)i * kk + j] = 0.0;
             });
         }
+        // aggregation sees the owned diagonal block only: aggregates never cross a rank boundary
+        Csr sq;
+        const Csr* Asq = Acur;
+        if (dist) { csr_select(c, *Acur, 0, n, 0, n, true, sq); Asq = &sq; }
         Csr S;
-        { Tick t(c, "strength graph"); strength_graph(c, *Acur, bs, par.theta, S); }
         DBuf<int> agg;
-        int n_agg;
-        { Tick t(c, "MIS(2) aggregation"); n_agg = aggregate_mis2(c, S, agg); }
-        if (n_agg == 0 || (double)n_agg * k >= 0.8 * n) break;
+        int n_agg = 0;
+        if (n > 0) {
+            { Tick t(c, "strength graph"); strength_graph(c, *Asq, bs, par.theta, S); }
+            { Tick t(c, "MIS(2) aggregation"); n_agg = aggregate_mis2(c, S, agg); }
+        }
+        sq = Csr();
+        std::vector<int64_t> coff;
+        int64_t nc_glob = (int64_t)n_agg * k;
+        if (dist) {
+            std::vector<int64_t> sizes;
+            const int64_t mine = (int64_t)n_agg * k;
+            dist_allgather_i64(c, &mine, 1, sizes);
+            coff.assign((size_t)c.nranks + 1, 0);
+            for (int r = 0; r < c.nranks; ++r) coff[r + 1] = coff[r] + sizes[r];
+            nc_glob = coff.back();
+        }
+        if (nc_glob == 0 || (double)nc_glob >= 0.8 * (double)n_glob) break;
         Csr T;
         DBuf<double> Bc;
-        { Tick t(c, "tentative prolongator"); tentative(c, agg, n_agg, n / bs, bs, k, B.p, T, Bc); }
+        if (n_agg > 0) { Tick t(c, "tentative prolongator"); tentative(c, agg, n_agg, n / bs, bs, k, B.p, T, Bc); }
+        else {
+            T.nrows = n; T.ncols = 0; T.nnz = 0;
+            T.rowptr.alloc((size_t)n + 1); T.rowptr.zero(c.stream); T.col.alloc(0); T.val.alloc(0);
+        }
         double omega = 4.0 / (3.0 * Lp->lmax / 1.1);
-        {
-            Csr AT;
-            { Tick t(c, "spgemm A*T"); csr_spgemm(c, *Acur, T, AT); }
-            csr_add_scaled(c, T, AT, -omega, Lp->dinv.p, Lp->P);
-        }
-        { Tick t(c, "transpose P"); csr_transpose(c, Lp->P, Lp->R); }
         Csr Ac;
-        {
-            Csr AP;
-            { Tick t(c, "spgemm A*P"); csr_spgemm(c, *Acur, Lp->P, AP); }
-            { Tick t(c, "spgemm R*(AP)"); csr_spgemm(c, Lp->R, AP, Ac); }
-        }
-        // dead coarse dofs (rank-deficient aggregates): unit diagonal
-        {
-            const int* rp = Ac.rowptr.p; const int* cc = Ac.col.p; double* v = Ac.val.p;
-            pfor(c, Ac.nrows, [=] __device__(int64_t i) {
-                for (int q = rp[i]; q < rp[i + 1]; ++q) if (cc[q] == (int)i && v[q] == 0.0) v[q] = 1.0;
-            });
+        if (!dist) {
+            {
+                Csr AT;
+                { Tick t(c, "spgemm A*T"); csr_spgemm(c, *Acur, T, AT); }
+                csr_add_scaled(c, T, AT, -omega, Lp->dinv.p, Lp->P);
+            }
+            { Tick t(c, "transpose P"); csr_transpose(c, Lp->P, Lp->R); }
+            {
+                Csr AP;
+                { Tick t(c, "spgemm A*P"); csr_spgemm(c, *Acur, Lp->P, AP); }
+                { Tick t(c, "spgemm R*(AP)"); csr_spgemm(c, Lp->R, AP, Ac); }
+            }
+            // dead coarse dofs (rank-deficient aggregates): unit diagonal
+            {
+                const int* rp = Ac.rowptr.p; const int* cc = Ac.col.p; double* v = Ac.val.p;
+                pfor(c, Ac.nrows, [=] __device__(int64_t i) {
+                    for (int q = rp[i]; q < rp[i + 1]; ++q) if (cc[q] == (int)i && v[q] == 0.0) v[q] = 1.0;
+                });
+            }
+        } else {
+            Tick t(c, "distributed P, Galerkin");
+            DistLevelOut o;
+            dist_amg_level(c, *Acur, *Lp->plan, T, coff, Lp->dinv.p, omega, o);
+            Lp->P = std::move(o.P);
+            Lp->R = std::move(o.R);
+            Ac = std::move(o.Ac);
+            next_plan = std::make_unique<DistPlan>(std::move(o.coarse_plan));
         }
         Lp->n_agg = n_agg;
         {
@@ -422,10 +495,36 @@ void Amg::setup(Ctx& c, const Csr& A, int bs, const double* B_dev, int k, const 
         B = std::move(Bc);
         bs = k;
     }
-    // coarsest level: dense inverse when small enough
-    const Csr& Ac = op((int)levels.size() - 1);
-    coarse_direct = Ac.nrows <= c.opt_i("poro_amg_dense_limit", 4096);
-    if (coarse_direct) { Tick t(c, "dense coarse inverse"); dense_inverse(c, Ac, coarse_inv); }
+    // coarsest level: dense inverse when small enough (gathered on every rank in a distributed hierarchy)
+    const int lc = (int)levels.size() - 1;
+    const Csr& Ac = op(lc);
+    coarse_n_global = rows_global(lc);
+    coarse_direct = !par.smoother_only && coarse_n_global <= c.opt_i("-poro_amg_dense_limit", 4096);
+    if (coarse_direct && !dist) { Tick t(c, "dense coarse inverse"); dense_inverse(c, Ac, coarse_inv); }
+    if (coarse_direct && dist) {
+        Tick t(c, "gathered dense coarse inverse");
+        const int ng = (int)coarse_n_global;
+        DistPlan& pl = *levels[lc]->plan;
+        DBuf<double> D((size_t)ng * ng);
+        D.zero(c.stream);
+        {
+            const int* rp = Ac.rowptr.p; const int* cc = Ac.col.p; const double* v = Ac.val.p; const int* gid = pl.ghost_gid.p;
+            double* d = D.p; const int no = pl.n_owned, off = (int)pl.offset;
+            pfor(c, Ac.nrows, [=] __device__(int64_t i) {
+                for (int q = rp[i]; q < rp[i + 1]; ++q) {
+                    const int col = cc[q] < no ? off + cc[q] : gid[cc[q] - no];
+                    d[(size_t)(off + (int)i) * ng + col] += v[q];
+                }
+            });
+        }
+        allreduce_sum(c, D.p, ng * ng);
+        DBuf<double> full;
+        dense_inverse_full(c, D.p, ng, full);
+        coarse_inv.alloc((size_t)pl.n_owned * ng);                       // this rank applies its rows of the inverse
+        if (pl.n_owned) PORO_CUDA(cudaMemcpyAsync(coarse_inv.p, full.p + (size_t)pl.offset * ng, (size_t)pl.n_owned * ng * sizeof(double),
+                                                  cudaMemcpyDeviceToDevice, c.stream));
+        coarse_full.alloc((size_t)ng);
+    }
     PORO_CUDA(cudaStreamSynchronize(c.stream));
 }
 
@@ -436,6 +535,18 @@ double Amg::complexity() const {
 }
 
 // ---- V-cycle --------------------------------------------------------------------------------
+const double* Amg::ext(int l, const double* v) {
+    if (!dist) return v;
+    Ctx& c = *ctx;
+    AmgLevel& L = *levels[l];
+    const int n = L.plan->n_owned;
+    double* dst;
+    if (v == L.x.p || v == L.r.p || v == L.d0.p || v == L.d1.p) dst = const_cast<double*>(v);   // stored extended: halo lands in place
+    else { vec_copy(c, L.ext.p, v, n); dst = L.ext.p; }
+    dist_halo_vec(c, *L.plan, dst, 1, dst + n);
+    return dst;
+}
+
 void Amg::cheby(int l, const double* b, double* x, bool zero_guess) {
     Ctx& c = *ctx;
     AmgLevel& L = *levels[l];
@@ -461,8 +572,7 @@ void Amg::cheby(int l, const double* b, double* x, bool zero_guess) {
             if (need_r) r[i] = bi;
         });
     } else {
-        if (l == 0 && fine_mat) spmv(c, *fine_mat, fine_extend(x), r, SPMV_SUB, b);
-        else spmv(c, A, x, r, SPMV_SUB, b);
+        spmv(c, A, ext(l, x), r, SPMV_SUB, b);
         pfor(c, n, [=] __device__(int64_t i) {
             double d = dinv[i] * r[i] * it;
             d_old[i] = d;
@@ -471,8 +581,7 @@ void Amg::cheby(int l, const double* b, double* x, bool zero_guess) {
     }
     for (int k = 1; k < deg; ++k) {
         double rho_new = 1.0 / (2.0 * sigma - rho);
-        if (l == 0 && fine_mat) spmv_cheb_step(c, *fine_mat, fine_extend(d_old), d_old, d_new, r, x, dinv, rho_new * rho, 2.0 * rho_new / delta);
-        else spmv_cheb_step(c, A, d_old, d_old, d_new, r, x, dinv, rho_new * rho, 2.0 * rho_new / delta);
+        spmv_cheb_step(c, A, ext(l, d_old), d_old, d_new, r, x, dinv, rho_new * rho, 2.0 * rho_new / delta);
         rho = rho_new;
         std::swap(d_old, d_new);
     }
@@ -484,7 +593,16 @@ void Amg::cycle(int l, const double* b, double* x) {
     const Csr& A = op(l);
     const int last = (int)levels.size() - 1;
     if (l == last) {
-        if (coarse_direct) dense_gemv(c, coarse_inv.p, A.nrows, b, x);
+        if (coarse_direct && !dist) dense_gemv(c, coarse_inv.p, A.nrows, b, x);
+        else if (coarse_direct) {
+            // gather the coarsest right-hand side on every rank (one small all-reduce), apply this rank's rows of the inverse
+            DistPlan& pl = *levels[l]->plan;
+            const int ng = (int)coarse_n_global;
+            coarse_full.zero(c.stream);
+            vec_copy(c, coarse_full.p + pl.offset, b, pl.n_owned);
+            allreduce_sum(c, coarse_full.p, ng);
+            dense_gemv_rect(c, coarse_inv.p, pl.n_owned, ng, coarse_full.p, x);
+        }
         else if (levels.size() == 1) cheby(l, b, x, true);            // `chebyshev` PC: one sweep of the full degree
         else { cheby(l, b, x, true); cheby(l, b, x, false); }
         return;
@@ -492,11 +610,10 @@ void Amg::cycle(int l, const double* b, double* x) {
     AmgLevel& L = *levels[l];
     AmgLevel& Ln = *levels[l + 1];
     cheby(l, b, x, true);
-    if (l == 0 && fine_mat) spmv(c, *fine_mat, fine_extend(x), L.r.p, SPMV_SUB, b);
-    else spmv(c, A, x, L.r.p, SPMV_SUB, b);
-    spmv(c, L.R, L.r.p, Ln.b.p);
+    spmv(c, A, ext(l, x), L.r.p, SPMV_SUB, b);
+    spmv(c, L.R, ext(l, L.r.p), Ln.b.p);                               // restriction reads the ghost residuals
     cycle(l + 1, Ln.b.p, Ln.x.p);
-    spmv(c, L.P, Ln.x.p, x, SPMV_ADD, x);
+    spmv(c, L.P, ext(l + 1, Ln.x.p), x, SPMV_ADD, x);                  // prolongation reads the ghost coarse values
     if (par.post_smooth) cheby(l, b, x, false);
 }
 

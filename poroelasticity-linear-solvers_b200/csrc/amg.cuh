@@ -13,6 +13,7 @@ struct AmgParams {
     double cheby_ratio = 10.0;
     int power_its = 15;
     int post_smooth = 1;        // 0: V(nu,0) cycle (non-symmetric: only under GMRES/FGMRES)
+    bool smoother_only = false; // `-*_pc_type chebyshev`: one level, no coarse solve of any kind
 };
 
 struct AmgLevel {
@@ -21,7 +22,12 @@ struct AmgLevel {
     double lmax = 1.0;
     int bs = 1;
     int n_agg = 0;
+    // work vectors; in a distributed hierarchy x, r, d0, d1 have room for [owned | ghost] so that the halo lands in place
     DBuf<double> x, b, r, d0, d1;
+    // distributed hierarchy: halo plan of this level's operator (level 0 borrows the plan of the block operator)
+    DistPlan* plan = nullptr;
+    std::unique_ptr<DistPlan> owned_plan;
+    DBuf<double> ext;               // staging for vectors that are not stored extended (the caller's x on level 0)
 };
 
 struct Amg {
@@ -31,18 +37,22 @@ struct Amg {
     const Csr* A0 = nullptr;        // finest operator is borrowed
     DBuf<double> coarse_inv;
     bool coarse_direct = false;
-    // row-partitioned runs: level-0 smoothing and residuals use the TRUE distributed operator (local rows x
-    // [owned | halo] columns) after a halo exchange; the transfer operators and coarse levels stay rank-local
-    const Csr* fine_mat = nullptr;
-    std::function<const double*(const double*)> fine_extend;
+    // row-partitioned runs (plan0 given): every level operator is distributed (local rows x [owned | ghost] columns),
+    // aggregates stay inside a rank, prolongator smoothing and the Galerkin product use the distributed operator
+    // (distamg.cu); the coarsest operator is gathered on every rank.  Without a plan the hierarchy is rank-local.
+    bool dist = false;
+    int64_t coarse_n_global = 0;
+    DBuf<double> coarse_full;       // gathered right-hand side of the coarsest level
     int prof_base = -1;             // phase-profile slot of level 0 (-1: not profiled)
 
     // B: device n x k row-major near-nullspace (may be null -> one constant per component)
-    void setup(Ctx& c, const Csr& A, int bs, const double* B_dev, int k, const AmgParams& p);
+    void setup(Ctx& c, const Csr& A, int bs, const double* B_dev, int k, const AmgParams& p, DistPlan* plan0 = nullptr);
     void apply(const double* b, double* x);     // x = V-cycle(b), zero initial guess
     const Csr& op(int l) const { return l == 0 ? *A0 : levels[l]->A; }
     double complexity() const;
 
+    const double* ext(int l, const double* v);   // [owned | ghost] view of a level-l vector, ghosts refreshed (collective)
+    int64_t rows_global(int l) const { return dist ? levels[l]->plan->offsets.back() : op(l).nrows; }
     void cheby(int l, const double* b, double* x, bool zero_guess);
     void cycle(int l, const double* b, double* x);
 };

@@ -90,6 +90,7 @@ int poro_ctx_destroy(poro_ctx* h) {
     cudaSetDevice(c.device);
     dist_finalize(c);
     for (auto e : c.prof.ev) cudaEventDestroy(e);
+    if (c.t0) { cudaEventDestroy(c.t0); cudaEventDestroy(c.t1); }
     if (c.h_pin) cudaFreeHost(c.h_pin);
     if (c.d_scal) cudaFree(c.d_scal);
     if (c.stream) cudaStreamDestroy(c.stream);
@@ -106,6 +107,26 @@ int poro_nccl_unique_id(unsigned char* id128) {
 int poro_ctx_init_dist(poro_ctx* h, int rank, int nranks, const unsigned char* id128) {
     API_BEGIN
     dist_init(h->c, rank, nranks, id128);
+    API_END
+}
+
+// CUDA-event stopwatch on the library's stream (bench.py: device-side time of the K timed steps)
+int poro_timer_start(poro_ctx* h) {
+    API_BEGIN
+    Ctx& c = h->c;
+    if (!c.t0) { PORO_CUDA(cudaEventCreate(&c.t0)); PORO_CUDA(cudaEventCreate(&c.t1)); }
+    PORO_CUDA(cudaEventRecord(c.t0, c.stream));
+    API_END
+}
+int poro_timer_stop(poro_ctx* h, double* ms) {
+    API_BEGIN
+    Ctx& c = h->c;
+    PORO_REQUIRE(c.t0 != nullptr, "poro_timer_stop without poro_timer_start");
+    PORO_CUDA(cudaEventRecord(c.t1, c.stream));
+    PORO_CUDA(cudaEventSynchronize(c.t1));
+    float f = 0.f;
+    PORO_CUDA(cudaEventElapsedTime(&f, c.t0, c.t1));
+    *ms = f;
     API_END
 }
 
@@ -330,7 +351,8 @@ static std::unique_ptr<MatOp> extract_block(poro_ctx* h, const Csr& Mp, int64_t 
     }
     op->n_owned_cols = pos;
     for (int t : col_fields) {
-        if (fl.nh[t]) {
+        // multi-rank: the exchange is collective, so a rank without ghosts of field t still takes part (it may have to send)
+        if (fl.nh[t] || c.nranks > 1) {
             for (int64_t i = 0; i < fl.nh[t]; ++i) cmap[fl.n_owned + fl.hoff[t] + i] = (int)(pos + i);
             op->pieces.push_back({&fl.halo[t], owned_pos[t], pos});
             pos += fl.nh[t];
@@ -375,11 +397,18 @@ static std::unique_ptr<KSP> make_inner(poro_ctx* h, MatOp* op, const std::string
     std::string pt = c.opt("-" + prefix + "pc_type", pc_type);
     if (pt == "fieldsplit") pt = "amg";
     const Csr* src = &op->mat();
-    if (pt == "hypre" || pt == "amg" || pt == "gamg" || pt == "chebyshev" || (pt == "lu" && src->nrows > c.opt_i("poro_dense_lu_limit", 8192))) {
-        // the AMG keeps a pointer to its finest operator: it must live as long as the KSP.  A square block
-        // (single rank) is used in place; otherwise the owned-column part is cut out and kept in owned_op.
+    const bool amg_type = pt == "hypre" || pt == "amg" || pt == "gamg" || pt == "ml" || pt == "chebyshev";
+    // row-partitioned runs: hierarchies are distributed (global Galerkin coarse levels, distamg.cu) whenever the block has
+    // ONE halo plan; the decision uses global sizes so that every rank takes the same (collective) path
+    DistPlan* plan = nullptr;
+    if (c.nranks > 1 && (amg_type || pt == "lu") && c.opt_i("-poro_amg_distributed", 1)) plan = op->plan_for_amg();
+    const int64_t rows_glob = plan ? plan->offsets.back() : src->nrows;
+    const bool big_lu = pt == "lu" && rows_glob > c.opt_i("-poro_dense_lu_limit", 8192);
+    if (amg_type || big_lu) {
+        // the AMG keeps a pointer to its finest operator: it must live as long as the KSP.  A square block (single rank) or
+        // a distributed block with its plan is used in place; otherwise the owned-column part is cut out and kept in owned_op.
         std::unique_ptr<MatOp> holder;
-        if (src->ncols != src->nrows) {
+        if (!plan && src->ncols != src->nrows) {
             holder = std::make_unique<MatOp>();
             holder->ctx = &c;
             local_square(c, *op, holder->M);
@@ -387,7 +416,7 @@ static std::unique_ptr<KSP> make_inner(poro_ctx* h, MatOp* op, const std::string
             holder->M.block_hint = bs;
             src = &holder->M;
         }
-        k->owned_pc = make_pc(c, pt, *src, bs, coords, cdim, prefix);
+        k->owned_pc = make_pc(c, pt, *src, bs, coords, cdim, prefix, plan);
         if (pt == "lu") {
             // "exact" block too large for a dense factorisation: iterate to tight tolerance instead
             k->type = c.opt("-" + prefix + "poro_exact_ksp_type", "gmres");
@@ -404,12 +433,6 @@ static std::unique_ptr<KSP> make_inner(poro_ctx* h, MatOp* op, const std::string
         k->owned_pc = make_pc(c, pt, *src, bs, coords, cdim, prefix);
     }
     k->pc = k->owned_pc.get();
-    if (PCAmg* a = dynamic_cast<PCAmg*>(k->pc)) {
-        if (c.nranks > 1 && op->mat().ncols != op->mat().nrows && c.opt_i("-poro_amg_distributed_smoother", 1)) {
-            a->amg.fine_mat = &op->mat();
-            a->amg.fine_extend = [op](const double* v) { return op->extended(v); };
-        }
-    }
     if (PCAmg* a = dynamic_cast<PCAmg*>(k->pc))
         a->amg.prof_base = prefix == "s_" ? 8 : (bs > 1 ? 16 : (prefix.find("fieldsplit") != std::string::npos ? 24 : -1));
     return k;
@@ -515,7 +538,21 @@ int poro_pc_setup(poro_ctx* h, poro_mat* A, poro_mat* P, poro_mat* P_diff, const
             sch->A10 = extract_block(h, *Pp, fl.off[t1], fl.off[t1] + fl.n[t1], {t0});
             sch->A11 = extract_block(h, *Pp, fl.off[t1], fl.off[t1] + fl.n[t1], {t1});
             (t0 == 1 ? sch->A00 : sch->A11)->M.block_hint = bs_v;
-            // selfp: S = A11 - A10 diag(A00)^-1 A01 on the local (owned) parts
+            // selfp: S = A11 - A10 diag(A00)^-1 A01
+            DistPlan* plan0 = nullptr;
+            DistPlan* plan1 = nullptr;
+            if (c.nranks > 1 && c.opt_i("-poro_amg_distributed", 1)) { plan0 = sch->A00->plan_for_amg(); plan1 = sch->A11->plan_for_amg(); }
+            if (plan0 && plan1) {
+                // row-partitioned: exact complement of the owned rows -- the A01 rows and the diagonal of the ghost dofs of split 0
+                // arrive by one sparse-row and one vector exchange; S gets its own (wider) halo plan
+                sch->S = std::make_unique<MatOp>();
+                sch->S->ctx = &c;
+                sch->S->dplan = std::make_unique<DistPlan>();
+                dist_selfp_schur(c, *plan0, *plan1, sch->A00->mat(), sch->A01->mat(), sch->A10->mat(), sch->A11->mat(), sch->S->M,
+                                 *sch->S->dplan);
+                sch->S->n_owned_cols = sch->n1;
+            } else
+            // single rank (or -poro_amg_distributed 0): from the local (owned) parts
             {
                 Csr a00, a01, a10, a11;
                 local_square(c, *sch->A00, a00);
@@ -658,6 +695,17 @@ int poro_pc_inner_solve(poro_pc* pc, const char* name, const double* r, double* 
     API_END
 }
 
+int poro_pc_inner_result(poro_pc* pc, const char* name, int* its, int* reason, double* rnorm) {
+    API_BEGIN
+    KSP* k = find_ksp(pc, name);
+    if (!k) throw Error(std::string("no such inner solver: ") + name);
+    PORO_CUDA(cudaStreamSynchronize(pc->ctx->c.stream));
+    if (its) *its = k->its;
+    if (reason) *reason = k->reason;
+    if (rnorm) *rnorm = k->rnorm;
+    API_END
+}
+
 int poro_pc_amg_info(poro_pc* pc, const char* name, int64_t* rows, int64_t* nnz, int cap, int* nlevels) {
     API_BEGIN
     KSP* k = find_ksp(pc, name);
@@ -684,7 +732,7 @@ static std::unique_ptr<MatOp> make_outer_op(poro_ctx* h, poro_mat* A) {
     } else permute_matrix(h, A->raw, op->M);
     op->n_owned_cols = fl.n_owned;
     for (int t = 0; t < 3; ++t)
-        if (fl.nh[t]) op->pieces.push_back({&fl.halo[t], fl.off[t], fl.n_owned + fl.hoff[t]});
+        if (fl.nh[t] || c.nranks > 1) op->pieces.push_back({&fl.halo[t], fl.off[t], fl.n_owned + fl.hoff[t]});
     if (!op->ref) csr_choose_lanes(op->M);
     // node-blocked s and f diagonal blocks (owned columns) -> BSR parts; everything else stays in one CSR remainder
     const int bd = fl.block_dim;
@@ -729,6 +777,7 @@ int poro_ksp_create(poro_ctx* h, poro_mat* A, poro_pc* pc, const char* type, dou
     s.type = type ? type : "gmres";
     s.rtol = rtol; s.atol = atol; s.dtol = divtol; s.max_it = maxit;
     if (restart > 0) s.restart = restart;
+    s.fields = &h->fl;
     s.set_from_options(prefix ? prefix : "global_");
     *out = k.release();
     API_END
@@ -744,6 +793,7 @@ int poro_ksp_solve(poro_ksp* k, const double* b, double* x, int* its, int* reaso
     else {
         if ((int64_t)k->bp.n < n) { k->bp.alloc(n); k->xp.alloc(n); }
         vec_gather(c, k->bp.p, b, fl.old_of_new.p, n);
+        if (k->ksp.guess_nonzero) vec_gather(c, k->xp.p, x, fl.old_of_new.p, n);
         k->ksp.solve(k->bp.p, k->xp.p);
         vec_scatter(c, x, k->xp.p, fl.old_of_new.p, n);
     }
@@ -761,6 +811,7 @@ int poro_ksp_solve_host(poro_ksp* k, const double* b_host, double* x_host, int* 
         PORO_CUDA(cudaSetDevice(c.device));
         if ((int64_t)k->bdev.n < n) { k->bdev.alloc(n); k->xdev.alloc(n); }
         PORO_CUDA(cudaMemcpyAsync(k->bdev.p, b_host, n * 8, cudaMemcpyHostToDevice, c.stream));
+        if (k->ksp.guess_nonzero) PORO_CUDA(cudaMemcpyAsync(k->xdev.p, x_host, n * 8, cudaMemcpyHostToDevice, c.stream));
     } catch (const std::exception& e) { g_err = e.what(); return -1; }
     int rc = poro_ksp_solve(k, k->bdev.p, k->xdev.p, its, reason, rnorm);
     if (rc) return rc;
@@ -775,6 +826,20 @@ int poro_ksp_residual_history(poro_ksp* k, double* out, int cap, int* n) {
     int m = (int)k->ksp.history.size();
     if (n) *n = m;
     for (int i = 0; i < m && i < cap; ++i) out[i] = k->ksp.history[i];
+    API_END
+}
+
+int poro_ksp_set_initial_guess_nonzero(poro_ksp* k, int flag) {
+    API_BEGIN
+    k->ksp.guess_nonzero = flag != 0;
+    API_END
+}
+
+int poro_ksp_field_history(poro_ksp* k, double* out, int cap, int* n) {
+    API_BEGIN
+    int m = (int)k->ksp.field_history.size();
+    if (n) *n = m;
+    for (int i = 0; i < m && i < cap; ++i) out[i] = k->ksp.field_history[i];
     API_END
 }
 

@@ -75,6 +75,20 @@ struct HaloField {
     int64_t n_halo = 0;
 };
 
+// ---- halo plan of one distributed matrix / AMG level (oracle/distamg_rank.py: Plan) -----------------------------
+// Rows are numbered rank-contiguously per level (`offsets`), local columns are [owned | ghost]; ghosts are ordered
+// neighbour-major and, inside one neighbour, in the order the owner sends them.
+struct DistPlan {
+    int64_t offset = 0;                   // global id of the first owned row
+    int n_owned = 0, n_ghost = 0;
+    std::vector<int64_t> offsets;         // nranks + 1
+    DBuf<int> ghost_gid;                  // global ids of the ghost columns (n_ghost)
+    std::vector<int> neigh;               // ranks we exchange with
+    std::vector<int64_t> send_ptr, recv_ptr;   // per neighbour, neigh.size() + 1 entries
+    DBuf<int> send_idx;                   // owned local indices to send, neighbour-major
+    DBuf<double> send_buf;                // packing scratch of the vector exchanges
+};
+
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -88,6 +102,7 @@ struct Ctx {
     double* d_scal = nullptr;    // device scratch for reductions
     static constexpr int kScal = 1 << 18;   // partials; +8192 doubles of small slots behind it
     int64_t launches = 0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;   // poro_timer_start / poro_timer_stop
     // phase profile: CUDA events on the launching stream, resolved lazily (no sync on the hot path)
     struct Prof {
         enum { kSlots = 40 };
@@ -104,17 +119,21 @@ struct Ctx {
     std::vector<int64_t> raw_send_ptr, raw_recv_count;
     std::vector<int32_t> raw_send_idx;
 
-    bool has_opt(const std::string& k) const { return opts.count(k) != 0; }
+    // keys are stored with their leading '-' (poro_options_set); look-ups accept both spellings
+    std::map<std::string, std::string>::const_iterator find_opt(const std::string& k) const {
+        return (!k.empty() && k[0] == '-') ? opts.find(k) : opts.find("-" + k);
+    }
+    bool has_opt(const std::string& k) const { return find_opt(k) != opts.end(); }
     std::string opt(const std::string& k, const std::string& def) const {
-        auto it = opts.find(k);
+        auto it = find_opt(k);
         return it == opts.end() ? def : it->second;
     }
     double opt_d(const std::string& k, double def) const {
-        auto it = opts.find(k);
+        auto it = find_opt(k);
         return it == opts.end() ? def : atof(it->second.c_str());
     }
     int opt_i(const std::string& k, int def) const {
-        auto it = opts.find(k);
+        auto it = find_opt(k);
         return it == opts.end() ? def : atoi(it->second.c_str());
     }
 };
@@ -209,6 +228,9 @@ void vec_maxpy_norm(Ctx& c, double* w, const double* V, int64_t ld, int ncol, co
 void vec_maxpy_host(Ctx& c, double* y, const double* V, int64_t ld, int ncol, const double* h_host, int64_t n);
 // sum over ranks in place (no-op on one rank), then copy to host and synchronise
 void allreduce_sum(Ctx& c, double* d_vals, int k);
+void allreduce_max(Ctx& c, double* d_vals, int k);
+// out[j] = max_i |x_j[i]| over nseg segments (lengths len[j]) of one vector; local to this rank
+void vec_amax_segments(Ctx& c, const double* x, const int64_t* off, const int64_t* len, int nseg, double* d_out);
 void fetch(Ctx& c, const double* d_vals, int k, double* host);
 double dot_host(Ctx& c, const double* x, const double* y, int64_t n);   // allreduced, synchronous
 double norm2_host(Ctx& c, const double* x, int64_t n);
@@ -242,6 +264,8 @@ void csr_to_host(const Csr& A, std::vector<int>& rp, std::vector<int>& ci, std::
 void csr_from_host(Ctx& c, int nrows, int ncols, const int64_t* rp, const int* ci, const double* v, Csr& out);
 // dense n x n inverse of a CSR matrix by Gauss-Jordan with partial pivoting (row-major result)
 void dense_inverse(Ctx& c, const Csr& A, DBuf<double>& inv);
+void dense_inverse_full(Ctx& c, const double* A_dense, int n, DBuf<double>& inv);
 void dense_gemv(Ctx& c, const double* M, int n, const double* x, double* y);
+void dense_gemv_rect(Ctx& c, const double* M, int nrows, int ncols, const double* x, double* y);   // M row-major nrows x ncols
 
 }  // namespace poro

@@ -12,7 +12,7 @@ namespace poro {
 
 typedef struct { char internal[128]; } ncclUniqueId_t;
 typedef void* ncclComm_p;
-enum { NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+enum { NCCL_INT8 = 0, NCCL_INT32 = 2, NCCL_INT64 = 4, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2 };
 
 struct NcclApi {
     void* lib = nullptr;
@@ -22,6 +22,7 @@ struct NcclApi {
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_p, cudaStream_t);
     int (*Send)(const void*, size_t, int, int, ncclComm_p, cudaStream_t);
     int (*Recv)(void*, size_t, int, int, ncclComm_p, cudaStream_t);
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_p, cudaStream_t);
     int (*GroupStart)();
     int (*GroupEnd)();
     const char* (*GetErrorString)(int);
@@ -45,6 +46,7 @@ static NcclApi* load_nccl() {
     SYM(AllReduce, "ncclAllReduce");
     SYM(Send, "ncclSend");
     SYM(Recv, "ncclRecv");
+    SYM(AllGather, "ncclAllGather");
     SYM(GroupStart, "ncclGroupStart");
     SYM(GroupEnd, "ncclGroupEnd");
     SYM(GetErrorString, "ncclGetErrorString");
@@ -89,6 +91,11 @@ void dist_allreduce_sum(Ctx& c, double* d_vals, int k) {
     NCCL_OK(c.nccl, c.nccl->AllReduce(d_vals, d_vals, (size_t)k, NCCL_FLOAT64, NCCL_SUM, (ncclComm_p)c.comm, c.stream));
 }
 
+void dist_allreduce_max(Ctx& c, double* d_vals, int k) {
+    if (c.nranks <= 1) return;
+    NCCL_OK(c.nccl, c.nccl->AllReduce(d_vals, d_vals, (size_t)k, NCCL_FLOAT64, NCCL_MAX, (ncclComm_p)c.comm, c.stream));
+}
+
 void dist_halo_exchange(Ctx& c, HaloField& hf, const double* x_owned, double* halo) {
     if (c.nranks <= 1 || c.neigh.empty()) return;
     int64_t nsend = hf.send_ptr.empty() ? 0 : hf.send_ptr.back();
@@ -102,6 +109,33 @@ void dist_halo_exchange(Ctx& c, HaloField& hf, const double* x_owned, double* ha
         if (nr) NCCL_OK(api, api->Recv(halo + hf.recv_ptr[k], (size_t)nr, NCCL_FLOAT64, c.neigh[k], (ncclComm_p)c.comm, c.stream));
     }
     NCCL_OK(api, api->GroupEnd());
+}
+
+// ---- set-up primitives of the distributed hierarchy (distamg.cu): grouped byte send/recv, all-gather of int64 --------
+void dist_group_begin(Ctx& c) {
+    if (c.nranks > 1) NCCL_OK(c.nccl, c.nccl->GroupStart());
+}
+void dist_group_end(Ctx& c) {
+    if (c.nranks > 1) NCCL_OK(c.nccl, c.nccl->GroupEnd());
+}
+void dist_send_bytes(Ctx& c, const void* dev, size_t bytes, int peer) {
+    NCCL_OK(c.nccl, c.nccl->Send(dev, bytes, NCCL_INT8, peer, (ncclComm_p)c.comm, c.stream));
+}
+void dist_recv_bytes(Ctx& c, void* dev, size_t bytes, int peer) {
+    NCCL_OK(c.nccl, c.nccl->Recv(dev, bytes, NCCL_INT8, peer, (ncclComm_p)c.comm, c.stream));
+}
+// all[r * count + i] = value i of rank r; synchronises the stream (set-up only)
+void dist_allgather_i64(Ctx& c, const int64_t* mine, int count, std::vector<int64_t>& all) {
+    all.assign((size_t)c.nranks * count, 0);
+    if (c.nranks <= 1) {
+        for (int i = 0; i < count; ++i) all[i] = mine[i];
+        return;
+    }
+    DBuf<int64_t> d_in((size_t)count), d_out((size_t)c.nranks * count);
+    PORO_CUDA(cudaMemcpyAsync(d_in.p, mine, (size_t)count * sizeof(int64_t), cudaMemcpyHostToDevice, c.stream));
+    NCCL_OK(c.nccl, c.nccl->AllGather(d_in.p, d_out.p, (size_t)count, NCCL_INT64, (ncclComm_p)c.comm, c.stream));
+    PORO_CUDA(cudaMemcpyAsync(all.data(), d_out.p, all.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, c.stream));
+    PORO_CUDA(cudaStreamSynchronize(c.stream));
 }
 
 }  // namespace poro

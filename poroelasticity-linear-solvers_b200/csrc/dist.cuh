@@ -7,6 +7,13 @@ void dist_get_unique_id(unsigned char* id128);
 void dist_init(Ctx& c, int rank, int nranks, const unsigned char* id128);
 void dist_finalize(Ctx& c);
 void dist_allreduce_sum(Ctx& c, double* d_vals, int k);
+void dist_allreduce_max(Ctx& c, double* d_vals, int k);
 // exchange one field's halo: gathers x[send_idx] into hf.send_buf, sends/receives, halo (n_halo doubles) filled
 void dist_halo_exchange(Ctx& c, HaloField& hf, const double* x_owned, double* halo);
+// set-up primitives (grouped point-to-point of raw bytes, all-gather of a few int64 per rank)
+void dist_group_begin(Ctx& c);
+void dist_group_end(Ctx& c);
+void dist_send_bytes(Ctx& c, const void* dev, size_t bytes, int peer);
+void dist_recv_bytes(Ctx& c, void* dev, size_t bytes, int peer);
+void dist_allgather_i64(Ctx& c, const int64_t* mine, int count, std::vector<int64_t>& all);
 }  // namespace poro

@@ -210,6 +210,12 @@ void csr_spgemm(Ctx& c, const Csr& A, const Csr& B, Csr& C) {
         C.nrows = n;
         return;
     }
+    if (parts.empty()) {                                   // no rows (a rank without coarse dofs)
+        C.nrows = n; C.ncols = B.ncols; C.nnz = 0;
+        C.rowptr.alloc((size_t)n + 1); C.rowptr.zero(c.stream); C.col.alloc(0); C.val.alloc(0);
+        csr_choose_lanes(C);
+        return;
+    }
     // concatenate row chunks
     int64_t nnz = 0;
     for (auto& p : parts) nnz += p.nnz;
@@ -476,6 +482,8 @@ __global__ void k_gj_elim(double* __restrict__ M, int n, int ld, int k, const do
     }
 }
 
+static void gauss_jordan(Ctx& c, DBuf<double>& M, int n, DBuf<double>& inv);
+
 void dense_inverse(Ctx& c, const Csr& A, DBuf<double>& inv) {
     const int n = A.nrows;
     PORO_REQUIRE(n == A.ncols, "dense_inverse: square matrix expected");
@@ -491,6 +499,26 @@ void dense_inverse(Ctx& c, const Csr& A, DBuf<double>& inv) {
             m[(size_t)i * l + nn + i] = 1.0;
         });
     }
+    gauss_jordan(c, M, n, inv);
+}
+
+// same from a dense row-major n x n matrix (the gathered coarsest operator of a distributed hierarchy)
+void dense_inverse_full(Ctx& c, const double* Ad, int n, DBuf<double>& inv) {
+    const int ld = 2 * n;
+    DBuf<double> M((size_t)n * ld);
+    {
+        double* m = M.p;
+        int nn = n, l = ld;
+        pfor(c, (int64_t)n * ld, [=] __device__(int64_t t) {
+            const int i = (int)(t / l), j = (int)(t % l);
+            m[t] = j < nn ? Ad[(size_t)i * nn + j] : (j - nn == i ? 1.0 : 0.0);
+        });
+    }
+    gauss_jordan(c, M, n, inv);
+}
+
+static void gauss_jordan(Ctx& c, DBuf<double>& M, int n, DBuf<double>& inv) {
+    const int ld = 2 * n;
     DBuf<int> piv(1);
     DBuf<double> colk((size_t)n), pivval(1);
     int gx = ceil_div(ld, 256);
@@ -511,12 +539,12 @@ void dense_inverse(Ctx& c, const Csr& A, DBuf<double>& inv) {
     PORO_CUDA(cudaStreamSynchronize(c.stream));
 }
 
-// y = M x, M row-major n x n: one warp per row
-__global__ void __launch_bounds__(256) k_gemv(const double* __restrict__ M, int n, const double* __restrict__ x,
+// y = M x, M row-major nrows x n: one warp per row
+__global__ void __launch_bounds__(256) k_gemv(const double* __restrict__ M, int nrows, int n, const double* __restrict__ x,
                                               double* __restrict__ y) {
     int row = (blockIdx.x * 256 + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
-    if (row >= n) return;
+    if (row >= nrows) return;
     const double* r = M + (size_t)row * n;
     double s = 0.0;
     for (int j = lane; j < n; j += 32) s = fma(r[j], x[j], s);
@@ -525,9 +553,11 @@ __global__ void __launch_bounds__(256) k_gemv(const double* __restrict__ M, int 
     if (lane == 0) y[row] = s;
 }
 
-void dense_gemv(Ctx& c, const double* M, int n, const double* x, double* y) {
-    if (n == 0) return;
-    k_gemv<<<ceil_div((int64_t)n * 32, 256), 256, 0, c.stream>>>(M, n, x, y);
+void dense_gemv(Ctx& c, const double* M, int n, const double* x, double* y) { dense_gemv_rect(c, M, n, n, x, y); }
+
+void dense_gemv_rect(Ctx& c, const double* M, int nrows, int ncols, const double* x, double* y) {
+    if (nrows == 0) return;
+    k_gemv<<<ceil_div((int64_t)nrows * 32, 256), 256, 0, c.stream>>>(M, nrows, ncols, x, y);
     PORO_LAUNCH_CHECK(c);
 }
 

@@ -20,26 +20,44 @@ namespace poro {
 // =============================================================================================
 // operators
 // =============================================================================================
+DistPlan* MatOp::plan_for_amg() {
+    Ctx& c = *ctx;
+    if (c.nranks <= 1) return nullptr;
+    if (dplan) return dplan.get();
+    if (amg_plan) return amg_plan.get();
+    if (pieces.size() != 1 || pieces[0].x_off != 0 || pieces[0].ext_off != mat().nrows) return nullptr;   // single-field square blocks only
+    amg_plan = std::make_unique<DistPlan>();
+    dist_plan_from_halo(c, *pieces[0].hf, mat().nrows, *amg_plan);
+    return amg_plan.get();
+}
+
 const double* MatOp::extended(const double* x) {
     Ctx& c = *ctx;
+    if (c.nranks > 1 && dplan) {
+        const int64_t next = mat().ncols;
+        if ((int64_t)xext.n < next) xext.alloc((size_t)next);
+        vec_copy(c, xext.p, x, dplan->n_owned);
+        dist_halo_vec(c, *dplan, xext.p, 1, xext.p + dplan->n_owned);
+        return xext.p;
+    }
     if (c.nranks <= 1 || pieces.empty()) return x;
     int64_t next = mat().ncols;
     if ((int64_t)xext.n < next) xext.alloc((size_t)next);
     vec_copy(c, xext.p, x, n_owned_cols);
     for (auto& p : pieces)
-        if (p.hf->n_halo) dist_halo_exchange(c, *p.hf, x + p.x_off, xext.p + p.ext_off);
+        dist_halo_exchange(c, *p.hf, x + p.x_off, xext.p + p.ext_off);    // collective: also with no ghosts of our own
     return xext.p;
 }
 
 void MatOp::apply(const double* x, double* y, SpmvMode mode, const double* z) {
     const Csr& A = mat();
-    if (A.nnz == 0 && mode != SPMV_SET) {           // structurally empty coupling block
-        if (y != z) vec_copy(*ctx, y, z, A.nrows);
-        return;
-    }
+    // the halo exchange is collective: every rank runs it, also one whose local block is empty
     const double* xe = extended(x);
     const bool prof = !parts.empty();
-    { ProfScope ps(*ctx, prof ? 32 : -1); spmv(*ctx, A, xe, y, mode, z); }
+    if (A.nnz == 0) {                               // structurally empty block (or everything lives in `parts`)
+        if (mode == SPMV_SET) vec_set(*ctx, y, 0.0, A.nrows);
+        else if (y != z) vec_copy(*ctx, y, z, A.nrows);
+    } else { ProfScope ps(*ctx, prof ? 32 : -1); spmv(*ctx, A, xe, y, mode, z); }
     int ip = 0;
     for (auto& p : parts) {
         double* yp = y + p->row_off;
@@ -87,11 +105,11 @@ static void rigid_body_modes(const double* coords, int64_t ndof, int dim, std::v
 }
 
 std::unique_ptr<PC> make_pc(Ctx& c, const std::string& pc_type, const Csr& A, int bs, const double* coords_host,
-                            int coord_dim, const std::string& prefix) {
+                            int coord_dim, const std::string& prefix, DistPlan* plan) {
     if (pc_type == "none") return std::make_unique<PCNone>(&c, A.nrows);
     if (pc_type == "jacobi") return std::make_unique<PCJacobi>(&c, A);
     bool want_lu = pc_type == "lu" || pc_type == "cholesky";
-    if (want_lu && A.nrows <= c.opt_i("poro_dense_lu_limit", 8192)) return std::make_unique<PCDense>(&c, A);
+    if (want_lu && !plan && A.nrows <= c.opt_i("-poro_dense_lu_limit", 8192)) return std::make_unique<PCDense>(&c, A);
     const bool cheb_only = pc_type == "chebyshev";      // Chebyshev(degree) on D^-1 A = a one-level hierarchy
     if (want_lu || cheb_only || pc_type == "hypre" || pc_type == "amg" || pc_type == "gamg" || pc_type == "ml") {
         auto pc = std::make_unique<PCAmg>();
@@ -104,6 +122,7 @@ std::unique_ptr<PC> make_pc(Ctx& c, const std::string& pc_type, const Csr& A, in
         p.post_smooth = c.opt_i("-" + prefix + "pc_amg_post_smooth", c.opt_i("-pc_amg_post_smooth", p.post_smooth));
         p.power_its = c.opt_i("-" + prefix + "pc_amg_power_its", c.opt_i("-pc_amg_power_its", p.power_its));
         if (cheb_only) {
+            p.smoother_only = true;       // Chebyshev(degree) at every size: never the dense coarse inverse
             p.max_levels = 1;
             p.cheby_degree = c.opt_i("-" + prefix + "pc_amg_cheby_degree", 4);
         }
@@ -114,9 +133,9 @@ std::unique_ptr<PC> make_pc(Ctx& c, const std::string& pc_type, const Csr& A, in
             rigid_body_modes(coords_host, A.nrows, coord_dim, B, k);
             DBuf<double> Bd(B.size());
             PORO_CUDA(cudaMemcpy(Bd.p, B.data(), B.size() * 8, cudaMemcpyHostToDevice));
-            pc->amg.setup(c, A, bs, Bd.p, k, p);
+            pc->amg.setup(c, A, bs, Bd.p, k, p, plan);
         } else {
-            pc->amg.setup(c, A, bs > 0 ? bs : 1, nullptr, bs > 0 ? bs : 1, p);
+            pc->amg.setup(c, A, bs > 0 ? bs : 1, nullptr, bs > 0 ? bs : 1, p, plan);
         }
         return pc;
     }
@@ -147,6 +166,13 @@ void KSP::set_from_options(const std::string& pre) {
     if (ref == "refine_always") cgs2 = true;
     if (ref == "refine_never") cgs2 = false;
     monitor = c.has_opt(key("ksp_monitor"));
+    converged_reason = c.has_opt(key("ksp_converged_reason"));
+    if (c.has_opt(key("ksp_initial_guess_nonzero"))) {
+        std::string v = c.opt(key("ksp_initial_guess_nonzero"), "");
+        guess_nonzero = !(v == "0" || v == "false" || v == "no");
+    }
+    monitor_fields = c.has_opt(key("ksp_monitor_fields"));
+    test_fields = c.has_opt(key("ksp_convergence_test_fields"));
     if (type == "fgmres") right = true;
 }
 
@@ -204,6 +230,51 @@ void KSP::solve(const double* b, double* x) {
     else throw Error("unsupported ksp type '" + type + "' (prefix " + prefix + ")");
     total_its += its;
     if (profile_op) profile_flush();
+    if (converged_reason && ctx->rank == 0) {
+        // PETSc's -ksp_converged_reason line (KSPConvergedReasonView)
+        const char* nm = reason == 2 ? "CONVERGED_RTOL" : reason == 3 ? "CONVERGED_ATOL" : reason == 4 ? "CONVERGED_ITS" :
+                         reason == -3 ? "DIVERGED_ITS" : reason == -4 ? "DIVERGED_DTOL" : reason == -5 ? "DIVERGED_BREAKDOWN" :
+                         reason == -8 ? "DIVERGED_INDEFINITE_PC" : reason == -9 ? "DIVERGED_NANORINF" :
+                         reason == -10 ? "DIVERGED_INDEFINITE_MAT" : "UNKNOWN";
+        printf("Linear %s solve %s due to %s iterations %d\n", prefix.c_str(), reason > 0 ? "converged" : "did not converge", nm, its);
+    }
+}
+
+// The revived `converged` callback of lib/Solver.py:8-51: per-field infinity norms of the TRUE residual b - A x_it,
+// normalised by max(||b_s||_2, ||b_f||_2, ||b_p||_2) (lib/Solver.py:17-18,125-127).  Returns 1 / -1 / 0 like the reference.
+int KSP::fields_test(const double* b, const double* xcur, int it) {
+    Ctx& c = *ctx;
+    const int64_t n = A->rows();
+    if ((int64_t)w3.n < n) w3.alloc(n);
+    double* ds = c.d_scal + Ctx::kScal + 4096 + 4096 - 32;
+    double h[3];
+    if (it == 0) {
+        const double* xs[3] = {b + fields->off[0], b + fields->off[1], b + fields->off[2]};
+        // three segment dots of different lengths: one launch each (set-up of the monitor, once per solve)
+        for (int t = 0; t < 3; ++t) {
+            if (fields->n[t] > 0) vec_dots(c, 1, &xs[t], &xs[t], fields->n[t], ds + t);
+            else PORO_CUDA(cudaMemsetAsync(ds + t, 0, sizeof(double), c.stream));
+        }
+        allreduce_sum(c, ds, 3);
+        fetch(c, ds, 3, h);
+        for (int t = 0; t < 3; ++t) b0_fields[t] = std::sqrt(h[t]);
+        field_history.clear();
+    }
+    if (xcur) A->apply(xcur, w3.p, SPMV_SUB, b); else vec_copy(c, w3.p, b, n);     // KSP.buildResidual (lib/Solver.py:19)
+    vec_amax_segments(c, w3.p, fields->off, fields->n, 3, ds);
+    allreduce_max(c, ds, 3);
+    fetch(c, ds, 3, h);
+    const double normalize = std::max(b0_fields[0], std::max(b0_fields[1], b0_fields[2]));
+    const double rr[3] = {h[0] / normalize, h[1] / normalize, h[2] / normalize};
+    for (int t = 0; t < 3; ++t) field_history.push_back(h[t]);
+    if (monitor_fields && c.rank == 0) {
+        if (it == 0) printf("KSP errors: %11s, %11s, %11s, %11s, %11s, %11s\n", "abs_s", "abs_f", "abs_p", "rel_s", "rel_f", "rel_p");
+        printf("KSP it %d:   %.5e, %.5e, %.5e, %.5e, %.5e, %.5e\n", it, h[0], h[1], h[2], rr[0], rr[1], rr[2]);
+    }
+    const double error_abs = std::max(h[0], std::max(h[1], h[2])), error_rel = std::max(rr[0], std::max(rr[1], rr[2]));
+    if (error_abs < atol || error_rel < rtol) return 1;
+    if (it > max_it || error_abs > dtol) return -1;
+    return 0;
 }
 
 void KSP::solve_gmres(const double* b, double* x, bool flexible) {
@@ -211,29 +282,61 @@ void KSP::solve_gmres(const double* b, double* x, bool flexible) {
     const int64_t n = A->rows();
     const bool rpc = right || flexible;
     const int m = std::max(1, std::min(restart, max_it));
+    const bool use_fields = fields && fields->set && (monitor_fields || test_fields);
     if (v_cols < m + 1 || (int64_t)V.n < (int64_t)(m + 1) * n) { V.alloc((size_t)(m + 1) * n); v_cols = m + 1; }
     if (flexible && (int64_t)Z.n < (int64_t)m * n) Z.alloc((size_t)m * n);
     if ((int64_t)w1.n < n) { w1.alloc(n); w2.alloc(n); }
+    DBuf<double> xtmp;
+    if (use_fields) xtmp.alloc(n);
     std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), hbuf(2 * (m + 1) + 2);
     auto Hm = [&](int i, int j) -> double& { return H[(size_t)i * m + j]; };
     double* d_h = c.d_scal + Ctx::kScal + 4096 + 16;   // [h (m+1) | h2 (m+1) | nrm2]; small-slot region
     PORO_REQUIRE(2 * (m + 1) + 2 <= 4096 - 16, "restart too large for the scalar scratch");
-    vec_set(c, x, 0.0, n);
+    if (!guess_nonzero) vec_set(c, x, 0.0, n);
     double rnorm0 = 0, ttol = 0;
     bool first = true;
     reason = 0;
     its = 0;
+    // xt += (correction of the current cycle after j steps): the Hessenberg least squares, then V y (through the PC for right PC)
+    auto add_correction = [&](double* xt, int j) {
+        if (j <= 0) return;
+        std::vector<double> y(j);
+        for (int i = j - 1; i >= 0; --i) {
+            double sum = g[i];
+            for (int q = i + 1; q < j; ++q) sum -= Hm(i, q) * y[q];
+            y[i] = sum / Hm(i, i);
+        }
+        if (flexible) vec_maxpy_host(c, xt, Z.p, n, j, y.data(), n);
+        else if (rpc) {
+            vec_set(c, w1.p, 0.0, n);
+            vec_maxpy_host(c, w1.p, V.p, n, j, y.data(), n);
+            pc->apply(w1.p, w2.p);
+            vec_axpy(c, xt, 1.0, w2.p, n);
+        } else vec_maxpy_host(c, xt, V.p, n, j, y.data(), n);
+    };
     while (reason == 0) {
         double* r = V.p;   // column 0
-        if (first) vec_copy(c, w1.p, b, n);
+        const bool zero_x = first && !guess_nonzero;
+        if (zero_x) vec_copy(c, w1.p, b, n);
         else A->apply(x, w1.p, SPMV_SUB, b);
         if (!rpc) pc->apply(w1.p, r); else vec_copy(c, r, w1.p, n);
         double beta = norm2_host(c, r, n);
         if (first) {
             history.push_back(beta);
-            reason = converged(beta, 0, rnorm0, ttol);
+            double bnorm = beta;
+            if (guess_nonzero) {
+                // PETSc's default test measures against ||b|| (preconditioned for left PC) when the guess is non-zero
+                if (!rpc) { pc->apply(b, w2.p); bnorm = norm2_host(c, w2.p, n); }
+                else bnorm = norm2_host(c, b, n);
+            }
+            reason = converged(bnorm, 0, rnorm0, ttol);
+            if (guess_nonzero) reason = beta != beta ? -9 : (beta <= ttol ? (beta < atol ? 3 : 2) : 0);
             first = false;
             if (monitor && c.rank == 0) printf("  %s KSP residual norm[%d] %.12e\n", prefix.c_str(), 0, beta);
+            if (use_fields) {
+                int t = fields_test(b, zero_x ? nullptr : x, 0);
+                if (test_fields) reason = t > 0 ? 2 : (t < 0 ? -4 : 0);
+            }
             if (reason) break;
         }
         if (beta == 0.0) { reason = 3; break; }
@@ -248,18 +351,20 @@ void KSP::solve_gmres(const double* b, double* x, bool flexible) {
             else if (rpc) { pc->apply(vj, w1.p); op_apply(w1.p, w); }
             else { op_apply(vj, w1.p); pc->apply(w1.p, w); }
             // classical Gram-Schmidt: one multi-dot pass, one multi-axpy(+norm) pass
-            ProfScope ps_gs(c, 5);
-            vec_mdot(c, V.p, n, j + 1, w, n, d_h, false);
-            allreduce_sum(c, d_h, j + 1);
-            vec_maxpy_norm(c, w, V.p, n, j + 1, d_h, n, d_h + 2 * (m + 1));
-            if (cgs2) {
-                double* d_h2 = d_h + (m + 1);
-                vec_mdot(c, V.p, n, j + 1, w, n, d_h2, false);
-                allreduce_sum(c, d_h2, j + 1);
-                vec_maxpy_norm(c, w, V.p, n, j + 1, d_h2, n, d_h + 2 * (m + 1));
+            {
+                ProfScope ps_gs(c, 5);
+                vec_mdot(c, V.p, n, j + 1, w, n, d_h, false);
+                allreduce_sum(c, d_h, j + 1);
+                vec_maxpy_norm(c, w, V.p, n, j + 1, d_h, n, d_h + 2 * (m + 1));
+                if (cgs2) {
+                    double* d_h2 = d_h + (m + 1);
+                    vec_mdot(c, V.p, n, j + 1, w, n, d_h2, false);
+                    allreduce_sum(c, d_h2, j + 1);
+                    vec_maxpy_norm(c, w, V.p, n, j + 1, d_h2, n, d_h + 2 * (m + 1));
+                }
+                allreduce_sum(c, d_h + 2 * (m + 1), 1);
+                fetch(c, d_h, 2 * (m + 1) + 1, hbuf.data());
             }
-            allreduce_sum(c, d_h + 2 * (m + 1), 1);
-            fetch(c, d_h, 2 * (m + 1) + 1, hbuf.data());
             for (int i = 0; i <= j; ++i) Hm(i, j) = hbuf[i] + (cgs2 ? hbuf[(m + 1) + i] : 0.0);
             double hn = std::sqrt(hbuf[2 * (m + 1)]);
             Hm(j + 1, j) = hn;
@@ -283,23 +388,15 @@ void KSP::solve_gmres(const double* b, double* x, bool flexible) {
             history.push_back(res);
             if (monitor && c.rank == 0) printf("  %s KSP residual norm[%d] %.12e\n", prefix.c_str(), its, res);
             reason = converged(res, its, rnorm0, ttol);
+            if (use_fields) {
+                vec_copy(c, xtmp.p, x, n);
+                add_correction(xtmp.p, j);
+                int t = fields_test(b, xtmp.p, its);
+                if (test_fields) reason = t > 0 ? 2 : (t < 0 ? -4 : 0);
+            }
             if (hn == 0.0 && reason == 0) reason = 2;
         }
-        if (j > 0) {
-            std::vector<double> y(j);
-            for (int i = j - 1; i >= 0; --i) {
-                double s = g[i];
-                for (int q = i + 1; q < j; ++q) s -= Hm(i, q) * y[q];
-                y[i] = s / Hm(i, i);
-            }
-            if (flexible) vec_maxpy_host(c, x, Z.p, n, j, y.data(), n);
-            else if (rpc) {
-                vec_set(c, w1.p, 0.0, n);
-                vec_maxpy_host(c, w1.p, V.p, n, j, y.data(), n);
-                pc->apply(w1.p, w2.p);
-                vec_axpy(c, x, 1.0, w2.p, n);
-            } else vec_maxpy_host(c, x, V.p, n, j, y.data(), n);
-        }
+        add_correction(x, j);
         if (reason == 0 && its >= max_it) reason = -3;
     }
     rnorm = history.empty() ? 0.0 : history.back();
@@ -310,7 +407,9 @@ __global__ void __launch_bounds__(256) k_cg_update(double* __restrict__ x, doubl
                                                    const double* __restrict__ p, const double* __restrict__ w,
                                                    const double* __restrict__ beta, const double* __restrict__ dpi,
                                                    int64_t n) {
-    const double a = *beta / *dpi;
+    const double d = *dpi;
+    if (!(d > 0.0)) return;      // indefinite operator (or NaN): leave x, r untouched; the host reports -10 / -9
+    const double a = *beta / d;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         x[i] = fma(a, p[i], x[i]);
@@ -354,7 +453,7 @@ void KSP::solve_cg(const double* b, double* x) {
         // w = A p ; dpi = p.w (fused); a = beta/dpi stays on the device
         {
             MatOp* mo = dynamic_cast<MatOp*>(A);
-            if (mo && c.nranks == 1) spmv_dot(c, mo->mat(), p, w, ds + 2);
+            if (mo && c.nranks == 1 && mo->parts.empty() && mo->pieces.empty()) spmv_dot(c, mo->mat(), p, w, ds + 2);
             else {
                 A->apply(p, w);
                 const double* xs[1] = {p};
@@ -379,7 +478,7 @@ void KSP::solve_cg(const double* b, double* x) {
             beta = h5[2];
             dp = natural_norm ? std::sqrt(std::fabs(beta)) : std::sqrt(h5[3]);
             PORO_CUDA(cudaMemcpyAsync(ds, dn, 2 * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
-            if (!(dpi > 0.0)) { reason = dpi != dpi ? -9 : -8; }
+            if (!(dpi > 0.0)) { reason = dpi != dpi ? -9 : -10; }   // KSP_DIVERGED_INDEFINITE_MAT
         }
         ++its;
         history.push_back(dp);

@@ -3,6 +3,7 @@
 #include "amg.cuh"
 #include "common.cuh"
 #include "dist.cuh"
+#include "distamg.cuh"
 
 namespace poro {
 
@@ -37,6 +38,11 @@ struct MatOp : LinOp {
     // halo pieces to refresh before the product: (plan, offset of the owned field slice inside x, offset in xext)
     struct Piece { HaloField* hf; int64_t x_off; int64_t ext_off; };
     std::vector<Piece> pieces;
+    // alternative to `pieces`: one plan for all ghost columns (assembled Schur complements, whose halo is wider than a field's)
+    std::unique_ptr<DistPlan> dplan;
+    // plan handed to a distributed AMG built on this block: dplan, or one derived from the single halo piece
+    std::unique_ptr<DistPlan> amg_plan;
+    DistPlan* plan_for_amg();
     int64_t n_owned_cols = 0;
     // node-blocked diagonal field blocks cut out of M and applied as BSR: y[row_off..] += B x[col_off..]
     struct DiagPart { Csr B; int64_t row_off, col_off; };
@@ -91,6 +97,14 @@ struct KSP {
     int max_it = 10000, restart = 30;
     bool right = false, unprec_norm = false, natural_norm = false, cgs2 = false;
     bool monitor = false;
+    bool converged_reason = false;      // -<prefix>ksp_converged_reason
+    bool guess_nonzero = false;         // KSPSetInitialGuessNonzero / -<prefix>ksp_initial_guess_nonzero (warm start over time steps)
+    // per-field infinity-norm residual monitor / convergence test: the `converged` callback of lib/Solver.py:8-51
+    // (dead code in the reference).  Needs the field layout; builds the true residual every iteration (GMRES only).
+    const Fields* fields = nullptr;
+    bool monitor_fields = false, test_fields = false;
+    double b0_fields[3] = {0, 0, 0};
+    std::vector<double> field_history;  // per iteration: abs_s, abs_f, abs_p
     // results
     int its = 0, reason = 0;
     double rnorm = 0.0;
@@ -115,6 +129,7 @@ struct KSP {
     void solve_gmres(const double* b, double* x, bool flexible);
     void solve_cg(const double* b, double* x);
     int converged(double rn, int it, double& rnorm0, double& ttol) const;
+    int fields_test(const double* b, const double* xcur, int it);
 };
 
 // PCFIELDSPLIT(schur) on the fp block (lib/Preconditioner.py:102-118, petsc-options-inexact:78-80)
@@ -182,6 +197,6 @@ struct AAR {   // lib/AAR.py:7-137
 
 // builds a PC of the requested PETSc-style type for a block
 std::unique_ptr<PC> make_pc(Ctx& c, const std::string& pc_type, const Csr& A, int bs, const double* coords_host,
-                            int coord_dim, const std::string& prefix);
+                            int coord_dim, const std::string& prefix, DistPlan* plan = nullptr);
 
 }  // namespace poro

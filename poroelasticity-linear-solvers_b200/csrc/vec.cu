@@ -301,10 +301,44 @@ void vec_maxpy_host(Ctx& c, double* y, const double* V, int64_t ld, int ncol, co
 }
 
 // ------------------------------------------------------------------------------------------
+// infinity norms of up to 4 segments of one vector (per-field residual monitor, lib/Solver.py:27-32)
+// ------------------------------------------------------------------------------------------
+struct Segs { int64_t off[4], len[4]; };
+__global__ void __launch_bounds__(kBlock) k_amax(const double* __restrict__ x, Segs sg, double* __restrict__ out) {
+    // one CTA per segment: monitors only, not a hot kernel
+    const int j = blockIdx.x;
+    __shared__ double sm[kBlock / 32];
+    double m = 0.0;
+    const double* p = x + sg.off[j];
+    for (int64_t i = threadIdx.x; i < sg.len[j]; i += kBlock) m = fmax(m, fabs(p[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kBlock / 32; ++w) t = fmax(t, sm[w]);
+        out[j] = t;
+    }
+}
+void vec_amax_segments(Ctx& c, const double* x, const int64_t* off, const int64_t* len, int nseg, double* d_out) {
+    PORO_REQUIRE(nseg >= 1 && nseg <= 4, "vec_amax_segments: 1..4 segments");
+    Segs sg;
+    for (int j = 0; j < 4; ++j) { sg.off[j] = off[j < nseg ? j : 0]; sg.len[j] = len[j < nseg ? j : 0]; }
+    k_amax<<<nseg, kBlock, 0, c.stream>>>(x, sg, d_out);
+    PORO_LAUNCH_CHECK(c);
+}
+
+// ------------------------------------------------------------------------------------------
 // cross-rank sum + host read-back
 // ------------------------------------------------------------------------------------------
 void allreduce_sum(Ctx& c, double* d_vals, int k) {
     if (c.nranks > 1 && !c.local_only) dist_allreduce_sum(c, d_vals, k);
+}
+
+void allreduce_max(Ctx& c, double* d_vals, int k) {
+    if (c.nranks > 1 && !c.local_only) dist_allreduce_max(c, d_vals, k);
 }
 
 void fetch(Ctx& c, const double* d_vals, int k, double* host) {

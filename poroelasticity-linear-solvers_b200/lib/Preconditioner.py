@@ -89,6 +89,12 @@ class PreconditionerCC(object):
     def inner_solve(self, name, r, z):
         _capi.check(self.ctx.lib.poro_pc_inner_solve(self.h, name.encode(), _capi._ptr(_tensor(r)), _capi._ptr(_tensor(z))))
 
+    def inner_result(self, name):
+        """(iterations, reason, residual norm) of the last application of an inner solver."""
+        its, reason, rnorm = C.c_int(), C.c_int(), C.c_double()
+        _capi.check(self.ctx.lib.poro_pc_inner_result(self.h, name.encode(), C.byref(its), C.byref(reason), C.byref(rnorm)))
+        return its.value, reason.value, rnorm.value
+
     def print_timings(self):
         s = self.stats()
         parprint("\n===== Timing preconditioner: {:.3f}s".format(s["t_total"]))

@@ -58,6 +58,19 @@ class _KSP:
         _capi.check(self.ctx.lib.poro_ksp_parts_info(self.h, b, f, 16, C.byref(n)))
         return [(b[i], f[i]) for i in range(n.value)]
 
+    def setInitialGuessNonzero(self, flag=True):
+        """petsc4py KSP.setInitialGuessNonzero (lib/Solver.py:94, commented out there): warm start over time steps."""
+        _capi.check(self.ctx.lib.poro_ksp_set_initial_guess_nonzero(self.h, int(bool(flag))))
+
+    def getFieldHistory(self):
+        """[(abs_s, abs_f, abs_p)] per iteration from the per-field monitor (lib/Solver.py:8-51)."""
+        n = C.c_int()
+        cap = 3 * (self.max_it + 2)
+        buf = (C.c_double * cap)()
+        _capi.check(self.ctx.lib.poro_ksp_field_history(self.h, buf, cap, C.byref(n)))
+        v = list(buf)[: min(n.value, cap)]
+        return [tuple(v[i:i + 3]) for i in range(0, len(v) - 2, 3)]
+
     def getIterationNumber(self):
         return self.its
 

@@ -54,9 +54,51 @@ dist.all_reduce(num)
 err = float(torch.sqrt(num[0] / num[1]))
 if rank == 0:
     print("ranks", world, "N", N, "its", ksp.its, "reason", ksp.reason, "spmv err %.2e" % err_spmv, "solution err %.2e" % err, flush=True)
-# iteration counts of the CPU twin of the row-partitioned preconditioner (oracle/ddamg.py, tests/test_oracle_ddamg.py)
-TWIN_ITS = {(8, 2): 49, (8, 4): 70}
-twin_ok = (N, world) not in TWIN_ITS or abs(ksp.its - TWIN_ITS[(N, world)]) <= max(2, TWIN_ITS[(N, world)] // 10)
+# iteration count of the CPU twin of the DISTRIBUTED hierarchies (oracle/distamg.py: uncoupled aggregation, distributed
+# prolongator smoothing + Galerkin product, halo-aware selfp Schur complement), and of the single-GPU algorithm
+twin_its = single_its = None
+if rank == 0:
+    import scipy.sparse as sp
+    from oracle.amg import SAAMG, rigid_body_modes
+    from oracle.blockpc import BlockPC, SchurLower, krylov_solver
+    from oracle.distamg import DistAmg
+    from oracle.krylov import gmres
+    from poro_b200.partition import slab_ranges
+
+    def slab_perm(coords, bs):
+        h2 = coords[:, 2].max() / (2 * N)
+        plane = np.rint(coords[::bs, 2] / h2).astype(int)
+        parts = [np.flatnonzero((plane >= a) & (plane < b)) for a, b in slab_ranges(2 * N + 1, world)]
+        perm = np.concatenate([(p[:, None] * bs + np.arange(bs)).ravel() for p in parts])
+        return perm, np.concatenate([[0], np.cumsum([len(p) * bs for p in parts])])
+
+    class Permuted:
+        def __init__(self, M, perm, off, bs, B, **kw):
+            self.perm = perm
+            self.h = DistAmg(sp.csr_matrix(M)[perm][:, perm].tocsr(), off, bs, None if B is None else B[perm], **kw)
+
+        def __call__(self, b):
+            y = np.empty_like(b)
+            y[self.perm] = self.h(b[self.perm])
+            return y
+
+    Bg = rigid_body_modes(glob.coords_s, 3)
+    perm_s, off_s = slab_perm(glob.coords_s, 3)
+    perm_p, off_p = slab_perm(glob.coords_p, 1)
+
+    def outer(mk_v, mk_p):
+        mkfp = lambda M: SchurLower(M, glob.nf, glob.np_, krylov_solver("preonly", mk_v), krylov_solver("preonly", mk_p), "f")
+        pcg = BlockPC(glob, {"s": krylov_solver("preonly", mk_v), "fp": mkfp})
+        return gmres(lambda v: glob.A @ v, glob.b, pcg, rtol=1e-10, atol=0.0, dtol=1e20, max_it=100, restart=100, pc_side="right")
+
+    twin_its = outer(lambda M: Permuted(M, perm_s, off_s, 3, Bg), lambda M: Permuted(M, perm_p, off_p, 1, None)).its
+    single_its = outer(lambda M: SAAMG(M, 3, Bg), lambda M: SAAMG(M, 1, None)).its
+    print("twin (distributed hierarchy on CPU) its", twin_its, " single-process hierarchy its", single_its, flush=True)
+twin_ok = True
+if rank == 0:
+    # same algorithm on both sides: +-10 % (the GPU builds its rigid-body modes about each rank's own centre);
+    # and the row partition must not cost more than 25 % over the single-GPU count
+    twin_ok = abs(ksp.its - twin_its) <= max(2, twin_its // 10) and ksp.its <= max(single_its + 2, int(1.25 * single_its))
 ok = err_spmv < 1e-13 and ksp.reason == 2 and err < 1e-8 and twin_ok
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)

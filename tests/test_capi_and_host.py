@@ -114,12 +114,6 @@ def test_next_sources_build(tmp_path):
         subprocess.run(["nvcc", "-O1", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "--extended-lambda",
                         "-c", s, "-o", out], check=True)
         assert os.path.getsize(out) > 0
-    # dist_prims.inc is written to be appended to dist.cu: compile it in that position
-    csrc = os.path.join(root, "poroelasticity-linear-solvers_b200", "csrc")
-    tu = tmp_path / "dist_tu.cu"
-    tu.write_text('#include "%s"\n#include "%s"\n' % (os.path.join(csrc, "dist.cu"), os.path.join(csrc, "next", "dist_prims.inc")))
-    subprocess.run(["nvcc", "-O1", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "--extended-lambda", "-I", csrc,
-                    "-c", str(tu), "-o", str(tmp_path / "dist_tu.o")], check=True)
     # and none of it is part of the shipped library
     build_py = open(os.path.join(root, "poroelasticity-linear-solvers_b200", "build.py")).read()
     assert "next/" not in build_py
