@@ -289,6 +289,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = get_context(local_rank)
     load_petsc_options(ctx, BENCH_OPTIONS, is_text=True)
+    extra = os.environ.get("PORO_EXTRA_OPTIONS", "").strip()        # A/B switches of library tunables (e.g. "-poro_bsr_tma 0")
+    if extra:
+        load_petsc_options(ctx, extra.replace(";", "\n"), is_text=True)
 
     # ---- set-up (untimed): assemble on the host, upload, build the preconditioner
     t_asm = time.perf_counter()
@@ -432,6 +435,8 @@ def main():
         "phases_ms_per_solve": {PHASE_NAMES.get(k, str(k)): round(v[0] / prof_steps, 3) for k, v in sorted(phases.items())},
         "clocks": clocks,
     }
+    if extra:
+        line["config"]["extra_options"] = extra
     if dom:
         traffic, traffic_src = measured_traffic("outer_part0", dom["bytes"])
         line["roofline"] = {"bound": "hbm", "kernel": "first node-blocked launch of the outer operator product (%s, rows of the solid field)" % dom["format"],

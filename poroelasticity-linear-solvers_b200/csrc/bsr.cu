@@ -207,11 +207,17 @@ bool bsr_from_csr(Ctx& c, const Csr& A, int BS, Bsr& out, double max_fill) {
     out.blk_row.alloc(blk.size());
     PORO_CUDA(cudaMemcpyAsync(out.blk_row.p, blk.data(), blk.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
     PORO_CUDA(cudaStreamSynchronize(c.stream));
+    // Blackwell path: chunked layout for the persistent TMA kernel; the plain arrays are only kept when it is unavailable
+    if (c.opt_i("-poro_bsr_tma", 1) && bsr_build_tma(c, out, rp)) {
+        out.val.release();
+        out.col.release();
+    }
     return true;
 }
 
 template <int MODE>
 int bsr_launch(Ctx& c, const Bsr& B, const double* x, double* y, const Epilogue& ep, double* dot_partial) {
+    if (B.t_ok) return bsr_tma_launch<MODE>(c, B, x, y, ep, dot_partial);
     const double a = B.nbrows ? (double)B.nnzb / B.nbrows : 0.0;
     const int G = a <= 1.5 ? 1 : a <= 4 ? 2 : a <= 12 ? 4 : a <= 48 ? 8 : a <= 160 ? 16 : 32;
 #define GO(BSS, GG)                                                                                                          \

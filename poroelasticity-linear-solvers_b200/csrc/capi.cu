@@ -758,6 +758,22 @@ static std::unique_ptr<MatOp> make_outer_op(poro_ctx* h, poro_mat* A) {
                 have_rem = true;
             }
         if (have_rem) { op->M = std::move(rem); op->ref = nullptr; }
+        // the mass couplings A_sf, A_fs = c M (x) I (lib/Assembler.py:83,88) share the node pattern of A_ss, A_ff: let each ride
+        // along its diagonal block as one scalar per block (one pass, one launch per field row instead of two)
+        if (c.opt_i("-poro_fuse_couplings", 1)) {
+            auto find = [&](int64_t r0, int64_t c0) -> int {
+                for (size_t i = 0; i < op->parts.size(); ++i) if (op->parts[i]->row_off == r0 && op->parts[i]->col_off == c0) return (int)i;
+                return -1;
+            };
+            for (int t = 0; t < 2; ++t) {
+                const int im = find(fl.off[t], fl.off[t]), ic = find(fl.off[t], fl.off[1 - t]);
+                if (im < 0 || ic < 0 || fl.n[0] != fl.n[1]) continue;
+                if (csr_fuse_coupling(c, op->parts[im]->B, op->parts[ic]->B)) {
+                    op->parts[im]->x2_off = op->parts[ic]->col_off;
+                    op->parts.erase(op->parts.begin() + ic);
+                }
+            }
+        }
     }
     return op;
 }
@@ -857,8 +873,8 @@ int poro_ksp_profile(poro_ksp* k, int enable, double* op_ms, int64_t* op_calls, 
             const Csr& B = p->B;
             if (B.bsr_state == 1) {
                 const Bsr& b = *B.bsr;
-                const int64_t ne = b.diag_only ? b.bs : b.bs * b.bs;
-                bytes += (8 * ne + 4) * b.nnzb + 4 * ((int64_t)b.nbrows + 1) + 16 * (int64_t)B.nrows + 8 * (int64_t)B.ncols;
+                const int64_t ne = (b.diag_only ? b.bs : b.bs * b.bs) + (p->x2_off >= 0 ? 1 : 0);
+                bytes += (8 * ne + 4) * b.nnzb + 4 * ((int64_t)b.nbrows + 1) + 16 * (int64_t)B.nrows + 8 * (int64_t)B.ncols * (p->x2_off >= 0 ? 2 : 1);
             } else bytes += 12 * B.nnz + 4 * ((int64_t)B.nrows + 1) + 16 * (int64_t)B.nrows + 8 * (int64_t)B.ncols;
         }
         *op_bytes = bytes;
@@ -879,9 +895,10 @@ int poro_ksp_parts_info(poro_ksp* k, int64_t* bytes, int* is_bsr, int cap, int* 
         const Csr& B = p->B;
         if (B.bsr_state == 1) {
             const Bsr& bb = *B.bsr;
-            const int64_t ne = bb.diag_only ? bb.bs : bb.bs * bb.bs;
-            b.push_back((8 * ne + 4) * bb.nnzb + 4 * ((int64_t)bb.nbrows + 1) + 16 * (int64_t)B.nrows + 8 * (int64_t)B.ncols);
-            f.push_back(bb.diag_only ? 2 : 1);
+            const bool fused = p->x2_off >= 0;
+            const int64_t ne = (bb.diag_only ? bb.bs : bb.bs * bb.bs) + (fused ? 1 : 0);
+            b.push_back((8 * ne + 4) * bb.nnzb + 4 * ((int64_t)bb.nbrows + 1) + 16 * (int64_t)B.nrows + 8 * (int64_t)B.ncols * (fused ? 2 : 1));
+            f.push_back(fused ? 3 : (bb.diag_only ? 2 : 1));
         } else {
             b.push_back(12 * B.nnz + 4 * ((int64_t)B.nrows + 1) + 16 * (int64_t)B.nrows + 8 * (int64_t)B.ncols);
             f.push_back(0);

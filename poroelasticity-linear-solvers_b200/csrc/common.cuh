@@ -186,6 +186,12 @@ struct Bsr {
     DBuf<double> val;
     DBuf<int> blk_row;
     int nblk = 0;
+    // chunked layout of the TMA kernel (bsr_tma.cu); when present the plain val / col arrays above are released
+    bool t_ok = false, t_fused = false;
+    int t_nchunk = 0;
+    int64_t t_blocks_padded = 0;
+    DBuf<int> t_desc, t_rp, t_col, t_colf;   // chunk descriptors (4 ints each), local row pointers, block columns (+ row mask)
+    DBuf<double> t_val, t_m;                 // values (32-interleaved per chunk); one coupling scalar per block (fused)
 };
 
 // ---- sparse matrix (device CSR, local rows) ---------------------------------------------------
@@ -239,6 +245,12 @@ double norm2_host(Ctx& c, const double* x, int64_t n);
 enum SpmvMode { SPMV_SET = 0, SPMV_SUB = 1, SPMV_ADD = 2 };   // y = Ax | y = z - Ax | y = z + Ax
 void csr_choose_lanes(Csr& A);
 void spmv(Ctx& c, const Csr& A, const double* x, double* y, SpmvMode mode = SPMV_SET, const double* z = nullptr);
+// converts a node-blocked matrix to BSR now (normally done lazily at the first product); true when BSR is in use
+bool csr_ensure_bsr(Ctx& c, const Csr& A);
+// tries to let the diagonal-block coupling C ride along the BSR form of A (same block rows / columns); on success
+// spmv_fused(A, x, x2, ...) computes A x + C x2 in one pass over A's blocks
+bool csr_fuse_coupling(Ctx& c, const Csr& A, const Csr& C);
+void spmv_fused(Ctx& c, const Csr& A, const double* x, const double* x2, double* y, SpmvMode mode = SPMV_SET, const double* z = nullptr);
 // fused Chebyshev step: t = A d_old; r -= t; d_new = c1 d_old + c2 dinv.*r; x += d_new
 void spmv_cheb_step(Ctx& c, const Csr& A, const double* x_in, const double* d_old, double* d_new, double* r, double* x,
                     const double* dinv, double c1, double c2);

@@ -62,7 +62,8 @@ void MatOp::apply(const double* x, double* y, SpmvMode mode, const double* z) {
     for (auto& p : parts) {
         double* yp = y + p->row_off;
         ProfScope ps(*ctx, 33 + ip++);
-        spmv(*ctx, p->B, xe + p->col_off, yp, mode == SPMV_SET ? SPMV_ADD : mode, yp);
+        if (p->x2_off >= 0) spmv_fused(*ctx, p->B, xe + p->col_off, xe + p->x2_off, yp, mode == SPMV_SET ? SPMV_ADD : mode, yp);
+        else spmv(*ctx, p->B, xe + p->col_off, yp, mode == SPMV_SET ? SPMV_ADD : mode, yp);
     }
 }
 

@@ -45,7 +45,8 @@ struct MatOp : LinOp {
     DistPlan* plan_for_amg();
     int64_t n_owned_cols = 0;
     // node-blocked diagonal field blocks cut out of M and applied as BSR: y[row_off..] += B x[col_off..]
-    struct DiagPart { Csr B; int64_t row_off, col_off; };
+    // x2_off >= 0: a mass coupling rides along B (bsr_tma.cu, FUSE): y[row_off..] += B x[col_off..] + C x[x2_off..]
+    struct DiagPart { Csr B; int64_t row_off, col_off; int64_t x2_off = -1; };
     std::vector<std::unique_ptr<DiagPart>> parts;
     DBuf<double> xext;
     int64_t rows() const override { return mat().nrows; }

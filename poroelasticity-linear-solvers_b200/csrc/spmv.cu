@@ -153,10 +153,30 @@ static void build_row_blocks(Ctx& c, const Csr& A) {
     PORO_CUDA(cudaStreamSynchronize(c.stream));
 }
 
-template <int MODE>
-static int launch_spmv(Ctx& c, const Csr& A, const double* x, double* y, const Epilogue& ep, double* dot_partial) {
-    if (A.nrows == 0) return 0;
-    if (A.block_hint > 1 && A.bsr_state < 0) {
+static void try_bsr(Ctx& c, const Csr& A);
+
+bool csr_ensure_bsr(Ctx& c, const Csr& A) {
+    if (A.block_hint > 1 && A.bsr_state < 0 && A.nrows > 0) try_bsr(c, A);
+    return A.bsr_state == 1;
+}
+
+bool csr_fuse_coupling(Ctx& c, const Csr& A, const Csr& C) {
+    if (!csr_ensure_bsr(c, A)) return false;
+    return bsr_fuse_coupling(c, *A.bsr, C);
+}
+
+void spmv_fused(Ctx& c, const Csr& A, const double* x, const double* x2, double* y, SpmvMode mode, const double* z) {
+    PORO_REQUIRE(A.bsr_state == 1 && A.bsr->t_fused, "spmv_fused: no fused coupling on this matrix");
+    Epilogue ep{};
+    ep.mode = mode;
+    ep.z = z;
+    if (mode == SPMV_SET) bsr_tma_launch<SPMV_SET>(c, *A.bsr, x, y, ep, nullptr, x2);
+    else if (mode == SPMV_SUB) bsr_tma_launch<SPMV_SUB>(c, *A.bsr, x, y, ep, nullptr, x2);
+    else bsr_tma_launch<SPMV_ADD>(c, *A.bsr, x, y, ep, nullptr, x2);
+}
+
+static void try_bsr(Ctx& c, const Csr& A) {
+    {
         // node-blocked matrix: convert once to BSR unless the blocks are mostly empty (e.g. M (x) I couplings)
         auto B = std::make_shared<Bsr>();
         int BS = A.block_hint % 3 == 0 ? 3 : (A.block_hint % 2 == 0 ? 2 : 0);
@@ -166,9 +186,15 @@ static int launch_spmv(Ctx& c, const Csr& A, const double* x, double* y, const E
             A.bsr_state = 1;
         } else A.bsr_state = 0;
         if (c.has_opt("-poro_verbose"))
-            fprintf(stderr, "    [spmv] %d x %d nnz=%lld hint=%d -> %s\n", A.nrows, A.ncols, (long long)A.nnz, A.block_hint,
-                    A.bsr_state == 1 ? "BSR" : "CSR");
+            fprintf(stderr, "    [spmv] %d x %d nnz=%lld hint=%d -> %s%s\n", A.nrows, A.ncols, (long long)A.nnz, A.block_hint,
+                    A.bsr_state == 1 ? "BSR" : "CSR", A.bsr_state == 1 && A.bsr->t_ok ? " (TMA chunks)" : "");
     }
+}
+
+template <int MODE>
+static int launch_spmv(Ctx& c, const Csr& A, const double* x, double* y, const Epilogue& ep, double* dot_partial) {
+    if (A.nrows == 0) return 0;
+    if (A.block_hint > 1 && A.bsr_state < 0) try_bsr(c, A);
     if (A.bsr_state == 1) return bsr_launch<MODE>(c, *A.bsr, x, y, ep, dot_partial);
     if (A.nblk < 0) build_row_blocks(c, A);
     int grid;

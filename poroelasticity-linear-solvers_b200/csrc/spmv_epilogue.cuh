@@ -44,6 +44,12 @@ __device__ __forceinline__ double block_sum_256(double v, double* sm) {
 }
 
 bool bsr_from_csr(Ctx& c, const Csr& A, int BS, Bsr& out, double max_fill);
+// bsr_tma.cu: chunked layout + persistent TMA kernel; `rp` = host copy of the block row pointers
+bool bsr_build_tma(Ctx& c, Bsr& B, const std::vector<int>& rp);
+// lets the diagonal-block coupling C (same block rows/columns as B) ride along B: y = B x + C x2 in one pass
+bool bsr_fuse_coupling(Ctx& c, Bsr& B, const Csr& C);
+template <int MODE>
+int bsr_tma_launch(Ctx& c, const Bsr& B, const double* x, double* y, const Epilogue& ep, double* dot_partial, const double* x2 = nullptr);
 template <int MODE>
 int bsr_launch(Ctx& c, const Bsr& B, const double* x, double* y, const Epilogue& ep, double* dot_partial);
 
