@@ -63,6 +63,10 @@ int poro_mat_info(poro_mat* m, int64_t* nrows, int64_t* ncols, int64_t* nnz);
 /* y = A x on the raw (un-permuted) matrix: Mat.mult / `matA * x` (lib/AAR.py:56,135); also the
  * SpMV micro-benchmark entry point. */
 int poro_mat_mult(poro_mat* m, const double* x_dev, double* y_dev);
+/* SpMV micro-benchmark of one uploaded matrix in one of the fused epilogue modes the solver uses (the reference's
+ * `mult` + `aypx(-1)` pairs, lib/Preconditioner.py:180-199): 0 y = A x, 1 y = z - A x, 2 y = z + A x, 3 Chebyshev step,
+ * 4 w = A p with p.w.  Returns the device time per launch (CUDA events on the library's stream). */
+int poro_mat_bench(poro_mat* m, int mode, int reps, double* ms_per_launch);
 
 /* ---- halo plan for row-partitioned runs (MatMult_MPIAIJ's VecScatter in the reference) ---
  * neighbours k = 0..nneigh-1: this rank sends x[send_idx[send_ptr[k]..send_ptr[k+1])] (owned,

@@ -35,6 +35,7 @@ SIGNATURES = {
     "poro_mat_destroy": [vp],
     "poro_mat_info": [vp, c_i64p, c_i64p, c_i64p],
     "poro_mat_mult": [vp, vp, vp],
+    "poro_mat_bench": [vp, C.c_int, C.c_int, c_f64p],
     "poro_halo_set": [vp, C.c_int64, C.c_int, vp, vp, vp, vp],
     "poro_fields_set": [vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int, C.c_int],
     "poro_fields_set_coords": [vp, C.c_int, vp, vp],
@@ -220,6 +221,12 @@ class Mat:
 
     def mult(self, x, y):
         check(self.ctx.lib.poro_mat_mult(self.h, _ptr(x), _ptr(y)))
+
+    def bench(self, mode: int, reps: int = 20) -> float:
+        """Device milliseconds per launch of the SpMV in epilogue mode 0..4 (see include/poro.h)."""
+        ms = C.c_double()
+        check(self.ctx.lib.poro_mat_bench(self.h, int(mode), int(reps), C.byref(ms)))
+        return ms.value
 
     def destroy(self):
         if self.h:

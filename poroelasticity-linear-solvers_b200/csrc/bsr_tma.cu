@@ -26,9 +26,11 @@ namespace poro {
 namespace {
 
 constexpr int kT = 256;        // threads per CTA
-constexpr int kCap = 512;      // blocks per chunk
 constexpr int kMaxR = 64;      // block rows per chunk (<= kT / 3 scalar rows: one epilogue row per thread)
-constexpr int kStages = 2;
+// pipeline shapes (blocks per chunk, ring stages, resident CTAs per SM); the layout is built for one of them
+// (-poro_bsr_tma_cfg): 0 = 512 / 2 / 2, 1 = 256 / 2 / 4, 2 = 256 / 3 / 3
+constexpr int kNumCfg = 3;
+constexpr int kCfgCap[kNumCfg] = {512, 256, 256};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -57,7 +59,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 
-template <int BS, bool DIAG, bool FUSE>
+template <int BS, bool DIAG, bool FUSE, int kCap, int kStages>
 struct TmaSmem {
     static constexpr int NE = DIAG ? BS : BS * BS;
     static constexpr int VAL_BYTES = kCap * NE * 8;
@@ -72,12 +74,12 @@ struct TmaSmem {
     static_assert(STAGE_BYTES % 16 == 0 && VAL_BYTES % 16 == 0 && COL_BYTES % 16 == 0 && RP_BYTES % 16 == 0, "TMA alignment");
 };
 
-template <int BS, int MODE, bool DIAG, bool FUSE>
-__global__ void __launch_bounds__(kT, 2)
+template <int BS, int MODE, bool DIAG, bool FUSE, int kCap, int kStages, int kMinB>
+__global__ void __launch_bounds__(kT, kMinB)
 k_bsr_tma(const int4* __restrict__ desc, int nchunk, const int* __restrict__ crp, const int* __restrict__ col,
           const double* __restrict__ val, const double* __restrict__ mval, const double* __restrict__ x,
           const double* __restrict__ x2, double* __restrict__ y, Epilogue ep, double* __restrict__ dot_partial, int G) {
-    using L = TmaSmem<BS, DIAG, FUSE>;
+    using L = TmaSmem<BS, DIAG, FUSE, kCap, kStages>;
     constexpr int NE = L::NE;
     extern __shared__ __align__(128) unsigned char smem[];
     double* part = reinterpret_cast<double*>(smem + kStages * L::STAGE_BYTES);
@@ -247,6 +249,8 @@ void pfor(Ctx& c, int64_t n, F f) {
 // ---------------------------------------------------------------------------------------------
 bool bsr_build_tma(Ctx& c, Bsr& B, const std::vector<int>& rp) {
     if (B.bs != 2 && B.bs != 3) return false;
+    B.t_cfg = std::max(0, std::min(kNumCfg - 1, c.opt_i("-poro_bsr_tma_cfg", 1)));
+    const int kCap = kCfgCap[B.t_cfg];
     const int nbr = B.nbrows;
     const int NE = B.diag_only ? B.bs : B.bs * B.bs;
     std::vector<int> desc;            // 4 ints per chunk: R0, block offset (padded space), row-pointer offset, nbr | cnt << 16
@@ -376,34 +380,43 @@ bool bsr_fuse_coupling(Ctx& c, Bsr& B, const Csr& C) {
 // ---------------------------------------------------------------------------------------------
 // launch
 // ---------------------------------------------------------------------------------------------
-template <int BS, int MODE, bool DIAG, bool FUSE>
-static void launch_one(Ctx& c, const Bsr& B, const double* x, const double* x2, double* y, const Epilogue& ep, double* dot_partial,
-                       int grid, int G) {
-    using L = TmaSmem<BS, DIAG, FUSE>;
+template <int BS, int MODE, bool DIAG, bool FUSE, int kCap, int kStages, int kMinB>
+static void launch_cfg(Ctx& c, const Bsr& B, const double* x, const double* x2, double* y, const Epilogue& ep, double* dot_partial, int G,
+                       int grid) {
+    using L = TmaSmem<BS, DIAG, FUSE, kCap, kStages>;
     static bool configured = false;
     if (!configured) {
-        PORO_CUDA(cudaFuncSetAttribute(k_bsr_tma<BS, MODE, DIAG, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        PORO_CUDA(cudaFuncSetAttribute(k_bsr_tma<BS, MODE, DIAG, FUSE, kCap, kStages, kMinB>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         configured = true;
     }
-    k_bsr_tma<BS, MODE, DIAG, FUSE><<<grid, kT, L::TOTAL, c.stream>>>(
+    k_bsr_tma<BS, MODE, DIAG, FUSE, kCap, kStages, kMinB><<<grid, kT, L::TOTAL, c.stream>>>(
         reinterpret_cast<const int4*>(B.t_desc.p), B.t_nchunk, B.t_rp.p, FUSE ? B.t_colf.p : B.t_col.p, B.t_val.p, FUSE ? B.t_m.p : nullptr,
         x, x2, y, ep, dot_partial, G);
+}
+
+template <int BS, int MODE, bool DIAG, bool FUSE>
+static void launch_one(Ctx& c, const Bsr& B, const double* x, const double* x2, double* y, const Epilogue& ep, double* dot_partial, int G,
+                       int grid) {
+    if (B.t_cfg == 0) launch_cfg<BS, MODE, DIAG, FUSE, 512, 2, 2>(c, B, x, x2, y, ep, dot_partial, G, grid);
+    else if (B.t_cfg == 1) launch_cfg<BS, MODE, DIAG, FUSE, 256, 2, 4>(c, B, x, x2, y, ep, dot_partial, G, grid);
+    else launch_cfg<BS, MODE, DIAG, FUSE, 256, 3, 3>(c, B, x, x2, y, ep, dot_partial, G, grid);
 }
 
 template <int MODE>
 int bsr_tma_launch(Ctx& c, const Bsr& B, const double* x, double* y, const Epilogue& ep, double* dot_partial, const double* x2) {
     const double a = B.nbrows ? (double)B.nnzb / B.nbrows : 0.0;
     const int G = a <= 1.5 ? 1 : a <= 4 ? 2 : a <= 12 ? 4 : a <= 48 ? 8 : a <= 160 ? 16 : 32;
-    const int grid = std::min(B.t_nchunk, 2 * c.sm_count);
     const bool fuse = x2 != nullptr && B.t_fused;
+    const int min_b = B.t_cfg == 0 ? 2 : (B.t_cfg == 1 ? 4 : 3);
+    const int grid = std::min(B.t_nchunk, min_b * c.sm_count);
     if (B.bs == 3) {
-        if (fuse) launch_one<3, MODE, false, true>(c, B, x, x2, y, ep, dot_partial, grid, G);
-        else if (B.diag_only) launch_one<3, MODE, true, false>(c, B, x, x2, y, ep, dot_partial, grid, G);
-        else launch_one<3, MODE, false, false>(c, B, x, x2, y, ep, dot_partial, grid, G);
+        if (fuse) launch_one<3, MODE, false, true>(c, B, x, x2, y, ep, dot_partial, G, grid);
+        else if (B.diag_only) launch_one<3, MODE, true, false>(c, B, x, x2, y, ep, dot_partial, G, grid);
+        else launch_one<3, MODE, false, false>(c, B, x, x2, y, ep, dot_partial, G, grid);
     } else {
-        if (fuse) launch_one<2, MODE, false, true>(c, B, x, x2, y, ep, dot_partial, grid, G);
-        else if (B.diag_only) launch_one<2, MODE, true, false>(c, B, x, x2, y, ep, dot_partial, grid, G);
-        else launch_one<2, MODE, false, false>(c, B, x, x2, y, ep, dot_partial, grid, G);
+        if (fuse) launch_one<2, MODE, false, true>(c, B, x, x2, y, ep, dot_partial, G, grid);
+        else if (B.diag_only) launch_one<2, MODE, true, false>(c, B, x, x2, y, ep, dot_partial, G, grid);
+        else launch_one<2, MODE, false, false>(c, B, x, x2, y, ep, dot_partial, G, grid);
     }
     PORO_LAUNCH_CHECK(c);
     return grid;

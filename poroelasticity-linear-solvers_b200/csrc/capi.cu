@@ -211,6 +211,40 @@ int poro_mat_mult(poro_mat* m, const double* x, double* y) {
     API_END
 }
 
+// micro-benchmark of one matrix in one epilogue mode: 0 y = A x, 1 y = z - A x, 2 y = z + A x, 3 fused Chebyshev step,
+// 4 w = A p with p.w; device time per launch by CUDA events on the library's stream (vectors are internal)
+int poro_mat_bench(poro_mat* m, int mode, int reps, double* ms_per_launch) {
+    API_BEGIN
+    Ctx& c = m->ctx->c;
+    const Csr& A = m->raw;
+    PORO_REQUIRE(A.nrows == A.ncols || mode <= 2, "Chebyshev / dot modes need a square matrix");
+    PORO_REQUIRE(mode >= 0 && mode <= 4 && reps > 0, "mode in 0..4, reps > 0");
+    const int64_t n = A.nrows, nc = A.ncols;
+    DBuf<double> x((size_t)nc), y((size_t)n), z((size_t)n), r((size_t)n), d1((size_t)n), dinv((size_t)n), xv((size_t)n);
+    vec_set(c, x.p, 1.0, nc); vec_set(c, z.p, 0.5, n); vec_set(c, r.p, 0.25, n); vec_set(c, dinv.p, 1e-3, n); vec_set(c, xv.p, 0.0, n);
+    auto once = [&]() {
+        if (mode == 0) spmv(c, A, x.p, y.p);
+        else if (mode == 1) spmv(c, A, x.p, y.p, SPMV_SUB, z.p);
+        else if (mode == 2) spmv(c, A, x.p, y.p, SPMV_ADD, z.p);
+        else if (mode == 3) spmv_cheb_step(c, A, x.p, x.p, d1.p, r.p, xv.p, dinv.p, 0.3, 0.1);
+        else spmv_dot(c, A, x.p, y.p, c.d_scal + Ctx::kScal + 4096);
+    };
+    for (int i = 0; i < 3; ++i) once();
+    cudaEvent_t e0, e1;
+    PORO_CUDA(cudaEventCreate(&e0));
+    PORO_CUDA(cudaEventCreate(&e1));
+    PORO_CUDA(cudaEventRecord(e0, c.stream));
+    for (int i = 0; i < reps; ++i) once();
+    PORO_CUDA(cudaEventRecord(e1, c.stream));
+    PORO_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    PORO_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_per_launch = ms / reps;
+    API_END
+}
+
 // ---------------------------------------------------------------------------------------------
 // halo plan and index sets
 // ---------------------------------------------------------------------------------------------
@@ -232,6 +266,7 @@ int poro_halo_set(poro_ctx* h, int64_t n_owned, int nneigh, const int32_t* neigh
     hf.send_buf.alloc(c.raw_send_idx.size());
     if (!c.raw_send_idx.empty())
         PORO_CUDA(cudaMemcpy(hf.send_idx.p, c.raw_send_idx.data(), c.raw_send_idx.size() * 4, cudaMemcpyHostToDevice));
+    if (c.nranks > 1) p2p_slots_setup(c, c.neigh, hf.send_ptr, hf.recv_ptr, hf.p2p);
     API_END
 }
 
@@ -315,6 +350,7 @@ int poro_fields_set(poro_ctx* h, const int64_t* is_s, int64_t ns, const int64_t*
         hf.send_idx.alloc(sidx.size());
         hf.send_buf.alloc(sidx.size());
         if (!sidx.empty()) PORO_CUDA(cudaMemcpy(hf.send_idx.p, sidx.data(), sidx.size() * 4, cudaMemcpyHostToDevice));
+        if (c.nranks > 1) p2p_slots_setup(c, c.neigh, hf.send_ptr, hf.recv_ptr, hf.p2p);     // collective (same order on every rank)
     }
     fl.set = true;
     API_END

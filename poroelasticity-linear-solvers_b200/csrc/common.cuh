@@ -65,6 +65,29 @@ struct DBuf {
 // ---- NCCL through dlopen (no link-time dependency; single-GPU runs never touch it) -------
 struct NcclApi;
 
+// ---- peer-to-peer halo slots (dist.cu: p2p_*) --------------------------------------------------------------------
+// Neighbour exchanges over NVLink without NCCL: a pack kernel STORES the boundary values straight into the neighbour's
+// receive region (CUDA-IPC mapped peer memory) and releases a sequence flag there; the receiver's kernel spins on its own
+// flags and copies the region behind its owned entries.  Regions are double-buffered by sequence parity; the sequence
+// numbers live in device memory so that the exchanges can be captured in CUDA graphs.
+struct P2PNeighDev {
+    double* peer_data[2];        // where this rank writes (neighbour's arena), per parity
+    uint32_t* peer_flag;         // neighbour's flag for messages from this rank
+    const double* my_data[2];    // where the neighbour writes (this rank's arena)
+    const uint32_t* my_flag;
+    int send_begin, send_end, recv_begin, recv_end;
+};
+struct P2PArgs {
+    P2PNeighDev nb[8];
+    int nn;
+};
+struct P2PSlots {
+    bool ready = false;
+    P2PArgs args{};
+    int nsend = 0, nrecv = 0;
+    uint32_t* d_state = nullptr;  // [push_seq, wait_seq, push_ticket, wait_ticket] in device memory
+};
+
 // ---- halo plan (per field after permutation) -----------------------------------------------
 struct HaloField {
     // for neighbour k: send owned entries send_idx[send_ptr[k]..send_ptr[k+1]) (field-local index),
@@ -73,6 +96,7 @@ struct HaloField {
     DBuf<int> send_idx;
     DBuf<double> send_buf;
     int64_t n_halo = 0;
+    P2PSlots p2p;
 };
 
 // ---- halo plan of one distributed matrix / AMG level (oracle/distamg_rank.py: Plan) -----------------------------
@@ -87,6 +111,7 @@ struct DistPlan {
     std::vector<int64_t> send_ptr, recv_ptr;   // per neighbour, neigh.size() + 1 entries
     DBuf<int> send_idx;                   // owned local indices to send, neighbour-major
     DBuf<double> send_buf;                // packing scratch of the vector exchanges
+    P2PSlots p2p;                         // NVLink peer-store path of the width-1 exchanges (when available)
 };
 
 struct Ctx {
@@ -97,6 +122,7 @@ struct Ctx {
     bool local_only = false;     // reductions stay on this rank (rank-local set-up such as the AMG power iteration)
     void* comm = nullptr;
     NcclApi* nccl = nullptr;
+    struct P2PState* p2p = nullptr;   // receive arena + mapped peer arenas (dist.cu)
     std::map<std::string, std::string> opts;
     double* h_pin = nullptr;     // pinned host scratch for scalar read-back
     double* d_scal = nullptr;    // device scratch for reductions
@@ -188,7 +214,7 @@ struct Bsr {
     int nblk = 0;
     // chunked layout of the TMA kernel (bsr_tma.cu); when present the plain val / col arrays above are released
     bool t_ok = false, t_fused = false;
-    int t_nchunk = 0;
+    int t_nchunk = 0, t_cfg = 0;
     int64_t t_blocks_padded = 0;
     DBuf<int> t_desc, t_rp, t_col, t_colf;   // chunk descriptors (4 ints each), local row pointers, block columns (+ row mask)
     DBuf<double> t_val, t_m;                 // values (32-interleaved per chunk); one coupling scalar per block (fused)

@@ -7,6 +7,8 @@
 // the library binds to whichever libnccl.so.2 the process already loaded (torch's).
 #include "dist.cuh"
 #include <dlfcn.h>
+#include <algorithm>
+#include <memory>
 
 namespace poro {
 
@@ -60,6 +62,9 @@ static NcclApi* load_nccl() {
         if (r__ != 0) throw Error(std::string("NCCL error: ") + (api)->GetErrorString(r__));     \
     } while (0)
 
+static void p2p_init(Ctx& c);
+static void p2p_finalize(Ctx& c);
+
 void dist_get_unique_id(unsigned char* id128) {
     NcclApi* api = load_nccl();
     ncclUniqueId_t id;
@@ -79,9 +84,11 @@ void dist_init(Ctx& c, int rank, int nranks, const unsigned char* id128) {
     NCCL_OK(api, api->CommInitRank(&comm, nranks, id, rank));
     c.comm = comm;
     c.nccl = api;
+    p2p_init(c);
 }
 
 void dist_finalize(Ctx& c) {
+    p2p_finalize(c);
     if (c.comm && c.nccl) c.nccl->CommDestroy((ncclComm_p)c.comm);
     c.comm = nullptr;
 }
@@ -98,6 +105,7 @@ void dist_allreduce_max(Ctx& c, double* d_vals, int k) {
 
 void dist_halo_exchange(Ctx& c, HaloField& hf, const double* x_owned, double* halo) {
     if (c.nranks <= 1 || c.neigh.empty()) return;
+    if (hf.p2p.ready) { p2p_exchange(c, hf.p2p, hf.send_idx.p, x_owned, halo); return; }
     int64_t nsend = hf.send_ptr.empty() ? 0 : hf.send_ptr.back();
     if (nsend) vec_gather(c, hf.send_buf.p, x_owned, hf.send_idx.p, nsend);
     NcclApi* api = c.nccl;
@@ -109,6 +117,184 @@ void dist_halo_exchange(Ctx& c, HaloField& hf, const double* x_owned, double* ha
         if (nr) NCCL_OK(api, api->Recv(halo + hf.recv_ptr[k], (size_t)nr, NCCL_FLOAT64, c.neigh[k], (ncclComm_p)c.comm, c.stream));
     }
     NCCL_OK(api, api->GroupEnd());
+}
+
+
+// =============================================================================================
+// NVLink peer-store halo exchange (no NCCL on the data path)
+// =============================================================================================
+struct P2PState {
+    unsigned char* arena = nullptr;            // this rank's receive arena (cudaMalloc, exported through CUDA IPC)
+    size_t bytes = 0, used = 0;
+    std::vector<unsigned char*> peer;          // mapped arenas of the other ranks (nullptr for self)
+    static constexpr size_t kFlagBytes = 1 << 16;   // head of the arena: 16 Ki sequence flags
+    int flags_used = 0;
+};
+
+static void p2p_finalize(Ctx& c) {
+    if (!c.p2p) return;
+    for (auto* q : c.p2p->peer) if (q) cudaIpcCloseMemHandle(q);
+    if (c.p2p->arena) cudaFree(c.p2p->arena);
+    delete c.p2p;
+    c.p2p = nullptr;
+}
+
+// Every rank exports its arena and maps all others'.  Collective; falls back (c.p2p stays null) when any rank fails.
+static void p2p_init(Ctx& c) {
+    if (c.nranks <= 1 || c.nranks > 9 || !c.opt_i("-poro_p2p", 1)) return;      // P2PArgs holds up to 8 neighbours
+    auto st = std::make_unique<P2PState>();
+    st->bytes = (size_t)c.opt_i("-poro_p2p_arena_mb", 512) << 20;
+    int64_t words[9] = {0};                       // [ok, 64-byte IPC handle]
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    bool ok = cudaMalloc(&st->arena, st->bytes) == cudaSuccess && cudaMemset(st->arena, 0, st->bytes) == cudaSuccess &&
+              cudaIpcGetMemHandle(&h, st->arena) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    words[0] = ok ? 1 : 0;
+    if (ok) memcpy(&words[1], &h, 64);
+    std::vector<int64_t> all;
+    dist_allgather_i64(c, words, 9, all);
+    for (int r = 0; r < c.nranks; ++r) ok = ok && all[(size_t)r * 9] == 1;
+    st->peer.assign((size_t)c.nranks, nullptr);
+    int64_t mine = 1;
+    if (ok) {
+        for (int r = 0; r < c.nranks && mine; ++r) {
+            if (r == c.rank) continue;
+            cudaIpcMemHandle_t hr;
+            memcpy(&hr, &all[(size_t)r * 9 + 1], 64);
+            void* q = nullptr;
+            if (cudaIpcOpenMemHandle(&q, hr, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); mine = 0; }
+            st->peer[r] = (unsigned char*)q;
+        }
+    } else mine = 0;
+    std::vector<int64_t> oks;
+    dist_allgather_i64(c, &mine, 1, oks);
+    for (int64_t v : oks) ok = ok && v == 1;
+    if (!ok) {
+        for (auto* q : st->peer) if (q) cudaIpcCloseMemHandle(q);
+        if (st->arena) cudaFree(st->arena);
+        if (c.has_opt("-poro_verbose") && c.rank == 0) fprintf(stderr, "  [dist] peer-to-peer halo path unavailable: NCCL send/recv is used\n");
+        return;
+    }
+    st->used = P2PState::kFlagBytes;
+    c.p2p = st.release();
+    if (c.has_opt("-poro_verbose") && c.rank == 0) fprintf(stderr, "  [dist] peer-to-peer halo path: %zu MB arena per rank, %d peers mapped\n", c.p2p->bytes >> 20, c.nranks - 1);
+}
+
+void p2p_slots_setup(Ctx& c, const std::vector<int>& neigh, const std::vector<int64_t>& send_ptr,
+                     const std::vector<int64_t>& recv_ptr, P2PSlots& slots) {
+    slots.ready = false;
+    if (!c.p2p || neigh.empty() || neigh.size() > 8) return;
+    P2PState& st = *c.p2p;
+    const size_t nn = neigh.size();
+    // my receive regions: two buffers (sequence parity) per neighbour, 128-byte aligned, plus one flag each
+    std::vector<int64_t> mine(2 * nn), theirs(2 * nn, 0);
+    for (size_t k = 0; k < nn; ++k) {
+        const size_t nr = (size_t)(recv_ptr[k + 1] - recv_ptr[k]);
+        const size_t need = ((nr * 8 + 127) & ~(size_t)127) * 2;
+        if (st.used + need > st.bytes || st.flags_used + 1 > (int)(P2PState::kFlagBytes / 4))
+            throw Error("peer-to-peer halo arena exhausted: raise -poro_p2p_arena_mb (or run with -poro_p2p 0)");
+        mine[2 * k] = (int64_t)st.used;
+        mine[2 * k + 1] = st.flags_used;
+        st.used += need;
+        st.flags_used += 1;
+    }
+    // tell every neighbour where it writes: grouped exchange of (offset, flag index)
+    DBuf<int64_t> d_mine(2 * nn), d_theirs(2 * nn);
+    PORO_CUDA(cudaMemcpyAsync(d_mine.p, mine.data(), 2 * nn * sizeof(int64_t), cudaMemcpyHostToDevice, c.stream));
+    dist_group_begin(c);
+    for (size_t k = 0; k < nn; ++k) {
+        dist_send_bytes(c, d_mine.p + 2 * k, 16, neigh[k]);
+        dist_recv_bytes(c, d_theirs.p + 2 * k, 16, neigh[k]);
+    }
+    dist_group_end(c);
+    PORO_CUDA(cudaMemcpyAsync(theirs.data(), d_theirs.p, 2 * nn * sizeof(int64_t), cudaMemcpyDeviceToHost, c.stream));
+    PORO_CUDA(cudaStreamSynchronize(c.stream));
+    slots.args.nn = (int)nn;
+    for (size_t k = 0; k < nn; ++k) {
+        P2PNeighDev& d = slots.args.nb[k];
+        const size_t nr = (size_t)(recv_ptr[k + 1] - recv_ptr[k]), ns = (size_t)(send_ptr[k + 1] - send_ptr[k]);
+        const size_t my_half = (nr * 8 + 127) & ~(size_t)127, peer_half = (ns * 8 + 127) & ~(size_t)127;
+        unsigned char* pa = st.peer[neigh[k]];
+        PORO_REQUIRE(pa != nullptr, "peer arena not mapped");
+        d.my_data[0] = (const double*)(st.arena + mine[2 * k]);
+        d.my_data[1] = (const double*)(st.arena + mine[2 * k] + my_half);
+        d.my_flag = (const uint32_t*)st.arena + mine[2 * k + 1];
+        d.peer_data[0] = (double*)(pa + theirs[2 * k]);
+        d.peer_data[1] = (double*)(pa + theirs[2 * k] + peer_half);
+        d.peer_flag = (uint32_t*)pa + theirs[2 * k + 1];
+        d.send_begin = (int)send_ptr[k]; d.send_end = (int)send_ptr[k + 1];
+        d.recv_begin = (int)recv_ptr[k]; d.recv_end = (int)recv_ptr[k + 1];
+    }
+    slots.nsend = (int)send_ptr[nn];
+    slots.nrecv = (int)recv_ptr[nn];
+    PORO_CUDA(cudaMalloc(&slots.d_state, 4 * sizeof(uint32_t)));     // lives as long as the process (a few bytes per plan)
+    PORO_CUDA(cudaMemsetAsync(slots.d_state, 0, 4 * sizeof(uint32_t), c.stream));
+    slots.ready = true;
+}
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// pack + push: boundary values go straight into the neighbours' receive regions; the last CTA to finish releases the flags
+__global__ void __launch_bounds__(256) k_p2p_push(P2PArgs a, const double* __restrict__ x, const int* __restrict__ send_idx,
+                                                  int nsend, uint32_t* __restrict__ state) {
+    const uint32_t seq = state[0] + 1u;
+    const int par = (int)(seq & 1u);
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < nsend; i += gridDim.x * 256) {
+        int k = 0;
+        while (k + 1 < a.nn && i >= a.nb[k].send_end) ++k;
+        a.nb[k].peer_data[par][i - a.nb[k].send_begin] = x[send_idx[i]];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(&state[2], 1u);
+        if (t == gridDim.x - 1) {
+            __threadfence_system();
+            for (int k = 0; k < a.nn; ++k)
+                if (a.nb[k].send_end > a.nb[k].send_begin) st_release_sys(a.nb[k].peer_flag, seq);
+            state[2] = 0u;
+            state[0] = seq;
+        }
+    }
+}
+
+// wait for the neighbours' flags, then move the received values behind the owned entries
+__global__ void __launch_bounds__(256) k_p2p_wait_copy(P2PArgs a, double* __restrict__ ghost, int nrecv, uint32_t* __restrict__ state) {
+    const uint32_t seq = state[1] + 1u;
+    const int par = (int)(seq & 1u);
+    if (threadIdx.x < a.nn) {
+        const P2PNeighDev& d = a.nb[threadIdx.x];
+        if (d.recv_end > d.recv_begin)
+            while ((int32_t)(ld_acquire_sys(d.my_flag) - seq) < 0) { }
+    }
+    __syncthreads();
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < nrecv; i += gridDim.x * 256) {
+        int k = 0;
+        while (k + 1 < a.nn && i >= a.nb[k].recv_end) ++k;
+        ghost[i] = __ldcv(a.nb[k].my_data[par] + (i - a.nb[k].recv_begin));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(&state[3], 1u);
+        if (t == gridDim.x - 1) { state[3] = 0u; state[1] = seq; }
+    }
+}
+
+void p2p_exchange(Ctx& c, P2PSlots& s, const int* send_idx, const double* x_owned, double* ghost_out) {
+    const int gs = std::max(1, std::min((s.nsend + 255) / 256, c.sm_count * 2));
+    const int gr = std::max(1, std::min((s.nrecv + 255) / 256, c.sm_count * 2));
+    k_p2p_push<<<gs, 256, 0, c.stream>>>(s.args, x_owned, send_idx, s.nsend, s.d_state);
+    PORO_LAUNCH_CHECK(c);
+    k_p2p_wait_copy<<<gr, 256, 0, c.stream>>>(s.args, ghost_out, s.nrecv, s.d_state);
+    PORO_LAUNCH_CHECK(c);
 }
 
 // ---- set-up primitives of the distributed hierarchy (distamg.cu): grouped byte send/recv, all-gather of int64 --------

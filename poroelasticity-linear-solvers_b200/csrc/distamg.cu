@@ -56,6 +56,7 @@ static int64_t scan_counts(Ctx& c, const int* in, int* out, int64_t n) {
 // ---- halo_vec: `width` doubles per row (vectors: 1) ------------------------------------------------------------------
 void dist_halo_vec(Ctx& c, DistPlan& plan, const double* x_owned, int width, double* ghost_out) {
     if (c.nranks <= 1) return;
+    if (width == 1 && plan.p2p.ready) { p2p_exchange(c, plan.p2p, plan.send_idx.p, x_owned, ghost_out); return; }
     const size_t nn = plan.neigh.size();
     const int64_t nsend = nn ? plan.send_ptr[nn] : 0;
     if (plan.send_buf.n < (size_t)nsend * width) plan.send_buf.alloc((size_t)nsend * width);
@@ -109,6 +110,7 @@ void dist_plan_from_halo(Ctx& c, const HaloField& hf, int64_t n_owned, DistPlan&
         pfor(c, plan.n_ghost, [=] __device__(int64_t i) { g[i] = (int)(s[i] + 0.5); });
     }
     PORO_CUDA(cudaStreamSynchronize(c.stream));
+    p2p_slots_setup(c, plan.neigh, plan.send_ptr, plan.recv_ptr, plan.p2p);
 }
 
 // ---- the handshake: all-gather how many ids every rank reads from every other, then send the id lists to their owners
@@ -160,6 +162,7 @@ void dist_plan_build(Ctx& c, const std::vector<int64_t>& offsets, DBuf<int>&& gh
         pfor(c, plan.send_ptr[nn], [=] __device__(int64_t i) { s[i] -= off; });
     }
     PORO_CUDA(cudaStreamSynchronize(c.stream));
+    p2p_slots_setup(c, plan.neigh, plan.send_ptr, plan.recv_ptr, plan.p2p);
 }
 
 // ---- halo_rows: the sparse rows of the boundary rows (GLOBAL column ids) ---------------------------------------------

@@ -26,6 +26,10 @@ from poro_b200.partition import distributed_problem
 
 ctx = get_context(local)
 load_petsc_options(ctx, AMG_OPTIONS, is_text=True)
+for opt in os.environ.get("PORO_EXTRA_OPTIONS", "").split(";"):      # e.g. "-poro_p2p 0;-poro_verbose"
+    if opt.strip():
+        kv = opt.split()
+        ctx.set_option(kv[0], kv[1] if len(kv) > 1 else None)
 prob = distributed_problem(3, N, "diagonal", rank, world, ctx)
 s, par = prob.sys, dict(prob.par)
 par.update({"solver rtol": 1e-10, "solver atol": 0.0, "solver maxiter": 100})

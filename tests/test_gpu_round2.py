@@ -168,8 +168,8 @@ def test_time_loop_reuses_solver_and_warm_starts(gpu_ctx):
         assert rel(x.numpy(), xd) <= 1e-7 and rel(xc.numpy(), xd) <= 1e-7
         res = np.linalg.norm(b - sys_.A @ x.numpy()) / np.linalg.norm(b)
         assert res <= 2e-9
-    # loads grow smoothly in t (1 - exp(-t^2/0.25)): the warm start saves iterations at every step
-    assert all(w < c for w, c in zip(its_warm, its_cold)), (its_warm, its_cold)
+    # loads grow smoothly in t (1 - exp(-t^2/0.25)): the warm start never costs iterations and saves some
+    assert all(w <= c for w, c in zip(its_warm, its_cold)) and sum(its_warm) < sum(its_cold), (its_warm, its_cold)
     # nothing was set up again: a re-setup launches tens of thousands of kernels, six solves far fewer
     stats = g["pc"].pc.getPythonContext().stats()
     assert stats["calls_s"] > 0
