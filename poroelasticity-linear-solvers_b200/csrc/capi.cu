@@ -636,6 +636,14 @@ int poro_pc_setup(poro_ctx* h, poro_mat* A, poro_mat* P, poro_mat* P_diff, const
         }
     }
     if (accel_order > 0) cc.anderson.init(&c, accel_order, fl.n_owned);
+    {
+        // CUDA graph of the application: only when it is a fixed launch sequence (no inner Krylov loop with host-side tests)
+        bool fixed = true;
+        for (KSP* k : {cc.ksp_s.get(), cc.ksp_f.get(), cc.ksp_p.get(), cc.ksp_fp.get(), cc.ksp_diff.get(),
+                       cc.schur ? cc.schur->k0.get() : nullptr, cc.schur ? cc.schur->k1.get() : nullptr})
+            if (k && k->type != "preonly") fixed = false;
+        cc.graph_enabled = fixed && c.opt_i("-poro_pc_graph", 1) != 0;
+    }
     // the permuted copy of P is no longer needed
     pc->Pperm = Csr();
     PORO_CUDA(cudaStreamSynchronize(c.stream));

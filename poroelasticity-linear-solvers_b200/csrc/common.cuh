@@ -128,6 +128,7 @@ struct Ctx {
     double* d_scal = nullptr;    // device scratch for reductions
     static constexpr int kScal = 1 << 18;   // partials; +8192 doubles of small slots behind it
     int64_t launches = 0;
+    std::vector<void*>* capture_log = nullptr;   // while a CUDA graph is being captured: the preonly KSPs that were applied
     cudaEvent_t t0 = nullptr, t1 = nullptr;   // poro_timer_start / poro_timer_stop
     // phase profile: CUDA events on the launching stream, resolved lazily (no sync on the hot path)
     struct Prof {

@@ -219,6 +219,7 @@ void KSP::solve(const double* b, double* x) {
     its = 0;
     reason = 0;
     if (type == "preonly") {
+        if (ctx->capture_log) ctx->capture_log->push_back(this);
         pc->apply(b, x);
         its = 1;
         reason = 4;
@@ -836,6 +837,47 @@ struct PhaseTimer {
 };
 
 void PCBlockCC::apply(const double* x, double* y) {
+    Ctx& c = *ctx;
+    const bool can_graph = graph_enabled && !c.prof.on && !timing && anderson.order == 0 && c.capture_log == nullptr;
+    if (!can_graph) { apply_impl(x, y); return; }
+    // the first application runs eagerly: it performs every lazy allocation and format conversion of the blocks
+    if (eager_calls < 1) { ++eager_calls; apply_impl(x, y); return; }
+    const int64_t n = fl->n_owned;
+    bool fresh = false;
+    if (!gexec) {
+        g_in.alloc((size_t)n);
+        g_out.alloc((size_t)n);
+        std::vector<void*> log;
+        const int64_t l0 = c.launches;
+        cudaGraph_t graph = nullptr;
+        PORO_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
+        c.capture_log = &log;
+        try {
+            apply_impl(g_in.p, g_out.p);
+        } catch (...) {
+            c.capture_log = nullptr;
+            cudaStreamEndCapture(c.stream, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            throw;
+        }
+        c.capture_log = nullptr;
+        PORO_CUDA(cudaStreamEndCapture(c.stream, &graph));
+        g_launches = c.launches - l0;
+        c.launches = l0;
+        PORO_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
+        cudaGraphDestroy(graph);
+        for (void* k : log) g_ksps.push_back(static_cast<KSP*>(k));
+        fresh = true;
+    }
+    vec_copy(c, g_in.p, x, n);
+    PORO_CUDA(cudaGraphLaunch(gexec, c.stream));
+    vec_copy(c, y, g_out.p, n);
+    c.launches += g_launches;
+    if (!fresh)
+        for (KSP* k : g_ksps) { k->calls++; k->total_its++; k->its = 1; k->reason = 4; }
+}
+
+void PCBlockCC::apply_impl(const double* x, double* y) {
     Ctx& c = *ctx;
     ProfScope ps_pc(c, 1);
     PhaseTimer tt(c, timing, t_total);

@@ -176,7 +176,18 @@ struct PCBlockCC : PC {
     // timings (seconds) like lib/Preconditioner.py:35-39; measured only when `poro_pc_timing` is set
     double t_total = 0, t_solid = 0, t_fluid = 0, t_press = 0, t_alloc = 0;
     bool timing = false;
+    // One application is a fixed sequence of kernels (and halo exchanges) whenever every inner solver is `preonly`: it is
+    // captured once into a CUDA graph and replayed, which removes the launch latency of the ~60 small kernels of the coarse
+    // AMG levels (the reference pays the same sequence as PETSc/hypre calls on the host, lib/Preconditioner.py:141-250).
+    bool graph_enabled = false;
+    int eager_calls = 0;
+    cudaGraphExec_t gexec = nullptr;
+    DBuf<double> g_in, g_out;
+    int64_t g_launches = 0;
+    std::vector<KSP*> g_ksps;
     void apply(const double* x, double* y) override;
+    void apply_impl(const double* x, double* y);
+    ~PCBlockCC() override { if (gexec) cudaGraphExecDestroy(gexec); }
     const char* kind() const override { return "blockcc"; }
 };
 
