@@ -268,6 +268,8 @@ def main():
     ap.add_argument("--cpu-sample-n", type=int, default=0, help="(unused since round 2: the CPU arm runs the GPU arm's own mesh)")
     ap.add_argument("--cpu-max-n", type=int, default=40, help="largest mesh the CPU oracle port is set up for")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--assemble", default="device", choices=["device", "host"],
+                    help="device: each rank generates its slab of A, P in HBM (csrc/gen.cu); host: hostfem element assembly + upload")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -293,17 +295,26 @@ def main():
     if extra:
         load_petsc_options(ctx, extra.replace(";", "\n"), is_text=True)
 
-    # ---- set-up (untimed): assemble on the host, upload, build the preconditioner
+    # ---- set-up (untimed): generate (or assemble) the system, build the preconditioner
     t_asm = time.perf_counter()
     N = mesh_for_gpus(args.mesh_n, world)
-    if world > 1:
+    gen_sys = None
+    if args.assemble == "device":
+        from poro_b200.generator import generate_swelling3d
+        gen_sys = generate_swelling3d(ctx, N, "diagonal", rank, world)
+        par, n_global = gen_sys.par, gen_sys.n_global
+        b_np, bcs_p = gen_sys.b, gen_sys.bcs_sub_pressure
+    elif world > 1:
         from poro_b200.partition import distributed_problem
         prob = distributed_problem(3, N, "diagonal", rank, world, ctx)
         sys_, par, n_global = prob.sys, prob.par, prob.n_global
+        b_np, bcs_p = sys_.b, sys_.bcs_sub_pressure
     else:
         from hostfem.problems import swelling     # host-side input generation standing in for FEniCS assembly (not the oracle)
         sys_, par = swelling(3, N, "diagonal")
         n_global = sys_.n
+        b_np, bcs_p = sys_.b, sys_.bcs_sub_pressure
+    ctx.sync()
     t_asm = time.perf_counter() - t_asm
     par = dict(par)
     # swelling-3d.py:66: maxiter (= restart, lib/Solver.py:99-100) 100, at every N: the distributed hierarchies
@@ -311,22 +322,26 @@ def main():
     maxiter = 100
     par.update({"solver rtol": RTOL, "solver atol": 0.0, "solver maxiter": maxiter, "solver type": "gmres"})
     t_set = time.perf_counter()
-    imap = IndexSet(sys_.is_s, sys_.is_f, sys_.is_p, two_way=True, block_dim=3, coords_s=sys_.coords_s,
-                    coords_p=sys_.coords_p) if world == 1 else prob.index_set()
-    dA, dP = DeviceMatrix(sys_.A, ctx), DeviceMatrix(sys_.P, ctx)
-    nnzA = sys_.A.nnz
-    b_host = torch.from_numpy(np.ascontiguousarray(sys_.b)).pin_memory()
+    if gen_sys is not None:
+        imap = gen_sys.index_set()
+        dA, dP = gen_sys.A, gen_sys.P
+        nnzA = gen_sys.A.nnz
+    else:
+        imap = IndexSet(sys_.is_s, sys_.is_f, sys_.is_p, two_way=True, block_dim=3, coords_s=sys_.coords_s,
+                        coords_p=sys_.coords_p) if world == 1 else prob.index_set()
+        dA, dP = DeviceMatrix(sys_.A, ctx), DeviceMatrix(sys_.P, ctx)
+        nnzA = sys_.A.nnz
+    b_host = torch.from_numpy(np.ascontiguousarray(b_np)).pin_memory()
     x_host = torch.zeros_like(b_host).pin_memory()
-    db = DeviceVector(sys_.b, ctx=ctx)
-    dx = DeviceVector(n=len(sys_.b), ctx=ctx)
-    pcw = Preconditioner(imap, dA, dP, None, par, sys_.bcs_sub_pressure)
+    db = DeviceVector(b_np, ctx=ctx)
+    dx = DeviceVector(n=len(b_np), ctx=ctx)
+    pcw = Preconditioner(imap, dA, dP, None, par, bcs_p)
     pc = pcw.get_pc()
     solver = Solver(dA, db, pc, par, imap)
     solver.create_solver(dA, db, pc)
     ksp = solver.solver
     ctx.sync()
     t_set = time.perf_counter() - t_set
-    A_host, b_np = sys_.A, sys_.b
 
     def barrier():
         if world > 1:
@@ -385,7 +400,7 @@ def main():
     phases = ctx.profile(0)
 
     # ---- verification of the timed result (outside the timed region): true residual on every N
-    dy = DeviceVector(n=len(sys_.b), ctx=ctx)
+    dy = DeviceVector(n=len(b_np), ctx=ctx)
     dA.mult(dx, dy)                                   # raw-ordering operator incl. halo exchange (poro_mat_mult)
     ctx.sync()
     r_loc = b_np - dy.numpy()
@@ -425,7 +440,7 @@ def main():
         "wall_ms_per_step": 1e3 * wall["dev"] / args.steps, "time_to_1e-8_s": t_solve, "its_per_solve": its / args.steps, "its_per_s": its / dt,
         "dof_its_per_s": n_global * its / dt,
         "reason": reason, "rnorm": rnorm, "true_rel_residual": true_res, "converged": bool(ok),
-        "setup_s": {"assembly_host": t_asm, "upload_and_pc_setup": t_set},
+        "setup_s": {"system_generation": t_asm, "generated_on": args.assemble, "pc_and_solver_setup": t_set},
         "inner": {k: v for k, v in stats.items() if k.startswith("its_") or k.startswith("calls_")},
         "e2e": {"value": n_global / t_solve_e if ok else None, "unit": UNIT, "h2d_bytes_per_step": int(b_host.numel() * 8),
                 "d2h_bytes_per_step": int(x_host.numel() * 8), "ms_per_step": 1e3 * t_solve_e},

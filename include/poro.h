@@ -68,6 +68,27 @@ int poro_mat_mult(poro_mat* m, const double* x_dev, double* y_dev);
  * 4 w = A p with p.w.  Returns the device time per launch (CUDA events on the library's stream). */
 int poro_mat_bench(poro_mat* m, int mode, int reps, double* ms_per_launch);
 
+int poro_mat_copy(poro_mat* m, int64_t* rowptr, int32_t* col, double* val);
+
+/* ---- device-side generator of the assembled system ------------------------------------
+ * Replaces the host assembly + DirichletBC.apply of lib/Assembler.py:66-221, lib/Poromechanics.py:76-83 on dolfin's
+ * UnitSquareMesh / UnitCubeMesh (lib/MeshCreation.py:11-19,169-178): every field block is one macro-cell matrix scattered
+ * over the cells, so a node's block row is one of a few class stencils, shifted.  `tables`: 9 entries, row-major over the
+ * field pairs (s, f, p) x (s, f, p); kr / kc: lattice of the row / column field (2 = P2 nodes, 1 = P1 nodes), br x bc
+ * values per entry, cls_ptr (ncls + 1), off = column-node offsets, vals; an empty block has cls_ptr == NULL.
+ * `layout` (22 int64): for the P1 then the P2 lattice [owned node range o0 o1 | lower-neighbour ghost range | upper-neighbour
+ * ghost range]; local dof offsets of the owned / lower-ghost / upper-ghost part of each field (3 + 3 + 3); local column
+ * count.  Rows are the owned nodes' dofs, field-major; `bc_flags_host`: one byte per local row (1 = Dirichlet) or NULL.
+ * The result is an ordinary poro_mat (local rows x [owned | ghost] columns). */
+typedef struct poro_gen_table {
+    int kr, kc, br, bc, diag_block, ncls;
+    const int32_t* cls_ptr;
+    const int64_t* off;
+    const double* vals;
+} poro_gen_table;
+int poro_gen_matrix(poro_ctx* ctx, int dim, int N, const poro_gen_table* tables, const int64_t* layout,
+                    const uint8_t* bc_flags_host, poro_mat** out);
+
 /* ---- halo plan for row-partitioned runs (MatMult_MPIAIJ's VecScatter in the reference) ---
  * neighbours k = 0..nneigh-1: this rank sends x[send_idx[send_ptr[k]..send_ptr[k+1])] (owned,
  * local numbering) to rank neigh[k] and receives recv_count[k] values which land, in the

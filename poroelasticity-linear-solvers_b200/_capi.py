@@ -36,6 +36,8 @@ SIGNATURES = {
     "poro_mat_info": [vp, c_i64p, c_i64p, c_i64p],
     "poro_mat_mult": [vp, vp, vp],
     "poro_mat_bench": [vp, C.c_int, C.c_int, c_f64p],
+    "poro_mat_copy": [vp, vp, vp, vp],
+    "poro_gen_matrix": [vp, C.c_int, C.c_int, vp, vp, vp, C.POINTER(vp)],
     "poro_halo_set": [vp, C.c_int64, C.c_int, vp, vp, vp, vp],
     "poro_fields_set": [vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int, C.c_int],
     "poro_fields_set_coords": [vp, C.c_int, vp, vp],

@@ -183,6 +183,29 @@ int poro_mat_create_csr(poro_ctx* h, int64_t nrows, int64_t ncols, const int64_t
     API_END
 }
 
+// helpers for gen.cu (the handle types are private to this file)
+poro_mat* poro_mat_adopt(poro_ctx* h, Csr&& A) {
+    auto m = std::make_unique<poro_mat>();
+    m->ctx = h;
+    m->raw = std::move(A);
+    m->raw.block_hint = h->c.opt_i("-poro_mat_block_hint", 0);
+    return m.release();
+}
+Ctx& poro_ctx_ref(poro_ctx* h) { return h->c; }
+void poro_set_error(const std::string& msg) { g_err = msg; }
+
+// copy of the raw local CSR to host arrays sized from poro_mat_info (tests of the device-side generator)
+int poro_mat_copy(poro_mat* m, int64_t* rowptr, int32_t* col, double* val) {
+    API_BEGIN
+    std::vector<int> rp, ci;
+    std::vector<double> v;
+    PORO_CUDA(cudaStreamSynchronize(m->ctx->c.stream));
+    csr_to_host(m->raw, rp, ci, v);
+    for (size_t i = 0; i < rp.size(); ++i) rowptr[i] = rp[i];
+    for (size_t i = 0; i < ci.size(); ++i) { col[i] = ci[i]; val[i] = v[i]; }
+    API_END
+}
+
 int poro_mat_destroy(poro_mat* m) {
     API_BEGIN
     delete m;
@@ -252,7 +275,7 @@ int poro_halo_set(poro_ctx* h, int64_t n_owned, int nneigh, const int32_t* neigh
                   const int32_t* send_idx, const int64_t* recv_count) {
     API_BEGIN
     Ctx& c = h->c;
-    c.n_owned_raw = n_owned;
+    c.n_owned_raw = nneigh > 0 ? n_owned : -1;       // no neighbours: back to the single-rank layout (everything is owned)
     c.neigh.assign(neigh, neigh + nneigh);
     c.raw_send_ptr.assign(send_ptr, send_ptr + nneigh + 1);
     c.raw_send_idx.assign(send_idx, send_idx + send_ptr[nneigh]);

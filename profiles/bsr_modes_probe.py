@@ -29,6 +29,8 @@ VARIANTS = [("ld.global.cs (bsr.cu)", {"-poro_bsr_tma": 0}), ("TMA 512x2, 2 CTA/
             ("TMA 256x2, 4 CTA/SM", {"-poro_bsr_tma_cfg": 1}), ("TMA 256x3, 3 CTA/SM", {"-poro_bsr_tma_cfg": 2})]
 if os.environ.get("PROBE_VARIANTS"):
     VARIANTS = [VARIANTS[int(i)] for i in os.environ["PROBE_VARIANTS"].split(",")]
+if os.environ.get("PROBE_MODES"):
+    MODES = {int(m): MODES[int(m)] for m in os.environ["PROBE_MODES"].split(",")}
 for name, opts in VARIANTS:
     ctx.clear_options()
     ctx.set_option("-poro_mat_block_hint", 3)
