@@ -23,27 +23,48 @@ namespace poro {
 static constexpr int kBlk = 256;
 static constexpr int kMaxBRows = 256;     // block rows per chunk (row pointers and row sums live in shared memory)
 
-template <int BS, int G, int MODE, bool DIAG, int kNtb>
-__global__ void __launch_bounds__(kBlk) k_bsr_stream(const int* __restrict__ blk_row, const int* __restrict__ rowptr,
+// PREF: the chunk has at most kBlk scalar rows, so every thread owns at most one epilogue row and loads its operands
+//       (z, or r / d / D^-1 / x of the Chebyshev step) at kernel START: they arrive while the blocks are streamed and
+//       multiplied instead of trailing the CTA (the tail that cost the Chebyshev-step launches 0.160 vs 0.135 ms).
+// FUSE: a mass coupling c M (x) I with the same block pattern rides along (one scalar per block in `mval`, a 3-bit row mask
+//       in the top bits of the column word): y = A x + C x2 in one pass.
+template <int BS, int MODE, bool DIAG, bool PREF, bool FUSE>
+__global__ void __launch_bounds__(kBlk, FUSE ? 3 : 4) k_bsr_stream(const int* __restrict__ blk_row, const int* __restrict__ rowptr,
                                                      const int* __restrict__ col, const double* __restrict__ val,
-                                                     const double* __restrict__ x, double* __restrict__ y, Epilogue ep,
-                                                     double* __restrict__ dot_partial) {
+                                                     const double* __restrict__ mval, const double* __restrict__ x,
+                                                     const double* __restrict__ x2, double* __restrict__ y, Epilogue ep,
+                                                     double* __restrict__ dot_partial, int G) {
+    constexpr int kNtb = 2;
     __shared__ double part[kBlk * kNtb * BS];
     __shared__ double rsum[kMaxBRows * BS];
     __shared__ int rp[kMaxBRows + 1];
     __shared__ double red[kBlk / 32];
     const int R0 = blk_row[blockIdx.x], R1 = blk_row[blockIdx.x + 1];
     const int nbr = R1 - R0;
+    // epilogue operands of this thread's row, requested before anything else
+    const bool has_row = PREF && (int)threadIdx.x < nbr * BS;
+    const int myrow = R0 * BS + threadIdx.x;
+    double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
+    if (has_row) {
+        if (MODE == SPMV_SUB || MODE == SPMV_ADD) e0 = ep.z[myrow];
+        else if (MODE == 3) { e0 = ep.r[myrow]; e1 = ep.d_old[myrow]; e2 = ep.dinv[myrow]; e3 = ep.xv[myrow]; }
+        else if (MODE == 4) e0 = x[myrow];
+    }
     for (int i = threadIdx.x; i <= nbr; i += kBlk) rp[i] = rowptr[R0 + i];
     __syncthreads();
     const int p0 = rp[0];
     const int cnt = rp[nbr] - p0;
     // phase 1: one thread per block
     int c[kNtb];
+    unsigned mk[kNtb];
+    double m[kNtb];
 #pragma unroll
     for (int t = 0; t < kNtb; ++t) {
         const int i = threadIdx.x + t * kBlk;
         c[t] = i < cnt ? __ldcs(col + p0 + i) : -1;
+        mk[t] = 0u;
+        m[t] = 0.0;
+        if (FUSE && c[t] >= 0) { mk[t] = (unsigned)c[t] >> 29; c[t] &= 0x1fffffff; m[t] = __ldcs(mval + p0 + i); }
     }
     constexpr int NE = DIAG ? BS : BS * BS;     // stored entries per block
     double v[kNtb][NE];
@@ -58,9 +79,13 @@ __global__ void __launch_bounds__(kBlk) k_bsr_stream(const int* __restrict__ blk
     for (int t = 0; t < kNtb; ++t) {
         const int i = threadIdx.x + t * kBlk;
         if (c[t] >= 0) {
-            double xv[BS];
+            double xv[BS], x2v[BS];
 #pragma unroll
             for (int j = 0; j < BS; ++j) xv[j] = __ldg(x + (size_t)c[t] * BS + j);
+            if (FUSE) {
+#pragma unroll
+                for (int j = 0; j < BS; ++j) x2v[j] = __ldg(x2 + (size_t)c[t] * BS + j);
+            }
 #pragma unroll
             for (int k = 0; k < BS; ++k) {
                 double s = 0.0;
@@ -69,15 +94,17 @@ __global__ void __launch_bounds__(kBlk) k_bsr_stream(const int* __restrict__ blk
 #pragma unroll
                     for (int j = 0; j < BS; ++j) s = fma(v[t][DIAG ? 0 : k * BS + j], xv[j], s);
                 }
+                if (FUSE && ((mk[t] >> k) & 1u)) s = fma(m[t], x2v[k], s);
                 part[i * BS + k] = s;
             }
         }
     }
     __syncthreads();
     // phase 2: G lanes per block row reduce the partial sums into rsum
+    const int lg = 31 - __clz(G);           // G is a power of two
     const int lane = threadIdx.x & (G - 1);
     const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
-    for (int Rl = threadIdx.x / G; Rl < nbr; Rl += kBlk / G) {
+    for (int Rl = threadIdx.x >> lg; Rl < nbr; Rl += kBlk >> lg) {
         const int a = rp[Rl] - p0, b = rp[Rl + 1] - p0;
         double s[BS];
 #pragma unroll
@@ -88,8 +115,7 @@ __global__ void __launch_bounds__(kBlk) k_bsr_stream(const int* __restrict__ blk
         }
 #pragma unroll
         for (int k = 0; k < BS; ++k) {
-#pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) s[k] += __shfl_down_sync(gmask, s[k], o, G);
+            for (int o = G >> 1; o > 0; o >>= 1) s[k] += __shfl_down_sync(gmask, s[k], o, G);
         }
         if (lane == 0) {
 #pragma unroll
@@ -99,7 +125,26 @@ __global__ void __launch_bounds__(kBlk) k_bsr_stream(const int* __restrict__ blk
     __syncthreads();
     // phase 3: coalesced epilogue over the scalar rows of the chunk
     double contrib = 0.0;
-    for (int rl = threadIdx.x; rl < nbr * BS; rl += kBlk) contrib += apply_epilogue<MODE>(ep, R0 * BS + rl, rsum[rl], x, y);
+    if (PREF) {
+        if (has_row) {
+            const double sum = rsum[threadIdx.x];
+            if (MODE == SPMV_SET) y[myrow] = sum;
+            else if (MODE == SPMV_SUB) y[myrow] = e0 - sum;
+            else if (MODE == SPMV_ADD) y[myrow] = e0 + sum;
+            else if (MODE == 3) {
+                const double rn = e0 - sum;
+                const double dn = ep.c1 * e1 + ep.c2 * e2 * rn;
+                ep.r[myrow] = rn;
+                ep.d_new[myrow] = dn;
+                ep.xv[myrow] = e3 + dn;
+            } else {
+                y[myrow] = sum;
+                contrib = sum * e0;
+            }
+        }
+    } else {
+        for (int rl = threadIdx.x; rl < nbr * BS; rl += kBlk) contrib += apply_epilogue<MODE>(ep, R0 * BS + rl, rsum[rl], x, y);
+    }
     if (MODE == 4) {
         double t = block_sum_256(contrib, red);
         if (threadIdx.x == 0) dot_partial[blockIdx.x] = t;
@@ -192,13 +237,18 @@ bool bsr_from_csr(Ctx& c, const Csr& A, int BS, Bsr& out, double max_fill) {
     // for diagonal blocks, 4 (0.086 vs 0.105 ms on A_sf)
     out.ntb = 2;
     (void)max_row;
+    // long block rows (the field blocks and their AMG levels): at most kBlk scalar rows per chunk, so that every thread owns
+    // one epilogue row and can request its operands up front (PREF); short rows (transfer operators) keep the wide chunks
+    const bool pref = (double)nnzb >= 6.0 * nbr && c.opt_i("-poro_bsr_prefetch", 1) != 0;
+    const int max_rows = pref ? kBlk / BS : kMaxBRows;
+    out.pref = pref;
     std::vector<int> blk;
     int r = 0;
     while (r < nbr) {
         blk.push_back(r);
         const int limit = rp[r] + kBlk * out.ntb;
         int hi = (int)(std::upper_bound(rp.begin() + r + 1, rp.end(), limit) - rp.begin()) - 1;
-        hi = std::min(hi, r + kMaxBRows);
+        hi = std::min(hi, r + max_rows);
         if (hi <= r) return false;                 // one block row longer than a chunk
         r = hi;
     }
@@ -208,37 +258,94 @@ bool bsr_from_csr(Ctx& c, const Csr& A, int BS, Bsr& out, double max_fill) {
     PORO_CUDA(cudaMemcpyAsync(out.blk_row.p, blk.data(), blk.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
     PORO_CUDA(cudaStreamSynchronize(c.stream));
     // Blackwell path: chunked layout for the persistent TMA kernel; the plain arrays are only kept when it is unavailable
-    if (c.opt_i("-poro_bsr_tma", 1) && bsr_build_tma(c, out, rp)) {
+    if (c.opt_i("-poro_bsr_tma", 0) && bsr_build_tma(c, out, rp)) {
         out.val.release();
         out.col.release();
     }
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------
+// fused mass coupling on the plain layout: one scalar per block + 3-bit row mask in the column word
+// ---------------------------------------------------------------------------------------------
+static bool bsr_fuse_coupling_plain(Ctx& c, Bsr& B, const Csr& C) {
+    if (B.diag_only || C.nrows != B.nbrows * B.bs || C.ncols != B.nbcols * B.bs || (int64_t)B.nbcols >= (1 << 29)) return false;
+    const int BS = B.bs;
+    DBuf<double> fm((size_t)B.nnzb);
+    DBuf<int> fcol((size_t)B.nnzb);
+    DBuf<unsigned long long> counters(2);      // [0] coupling entries matched, [1] violations of the c M_IJ I x mask form
+    counters.zero(c.stream);
+    {
+        const int* brp = B.rowptr.p; const int* bc = B.col.p; int* oc = fcol.p; double* om = fm.p;
+        const int* crp = C.rowptr.p; const int* ccol = C.col.p; const double* cv = C.val.p;
+        unsigned long long* cnts = counters.p;
+        pfor(c, (int64_t)B.nbrows * 32, [=] __device__(int64_t gt) {
+            const int I = (int)(gt >> 5), ln = (int)(gt & 31);
+            unsigned long long matched = 0, bad = 0;
+            for (int p = brp[I] + ln; p < brp[I + 1]; p += 32) {
+                const int J = bc[p];
+                double m = 0.0;
+                unsigned mask = 0u;
+                for (int q = 0; q < BS; ++q) {
+                    const int row = I * BS + q, want = J * BS + q;
+                    int lo = crp[row], hi = crp[row + 1];
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ccol[mid] < want) lo = mid + 1; else hi = mid; }
+                    if (lo < crp[row + 1] && ccol[lo] == want) {
+                        const double v = cv[lo];
+                        matched++;
+                        if (v != 0.0) {
+                            if (mask == 0u) m = v;
+                            else if (v != m) bad++;
+                            mask |= 1u << q;
+                        }
+                    }
+                }
+                om[p] = m;
+                oc[p] = J | (int)(mask << 29);
+            }
+            if (matched) atomicAdd(cnts, matched);
+            if (bad) atomicAdd(cnts + 1, bad);
+        });
+    }
+    unsigned long long h[2] = {0, 0};
+    PORO_CUDA(cudaMemcpyAsync(h, counters.p, sizeof h, cudaMemcpyDeviceToHost, c.stream));
+    PORO_CUDA(cudaStreamSynchronize(c.stream));
+    if (h[1] != 0 || (int64_t)h[0] != C.nnz) return false;
+    B.f_m = std::move(fm);
+    B.f_col = std::move(fcol);
+    B.fused = true;
+    return true;
+}
+
+bool bsr_fuse_coupling(Ctx& c, Bsr& B, const Csr& C) {
+    return B.t_ok ? bsr_fuse_coupling_tma(c, B, C) : bsr_fuse_coupling_plain(c, B, C);
+}
+
 template <int MODE>
-int bsr_launch(Ctx& c, const Bsr& B, const double* x, double* y, const Epilogue& ep, double* dot_partial) {
-    if (B.t_ok) return bsr_tma_launch<MODE>(c, B, x, y, ep, dot_partial);
+int bsr_launch(Ctx& c, const Bsr& B, const double* x, double* y, const Epilogue& ep, double* dot_partial, const double* x2) {
+    if (B.t_ok) return bsr_tma_launch<MODE>(c, B, x, y, ep, dot_partial, x2);
     const double a = B.nbrows ? (double)B.nnzb / B.nbrows : 0.0;
     const int G = a <= 1.5 ? 1 : a <= 4 ? 2 : a <= 12 ? 4 : a <= 48 ? 8 : a <= 160 ? 16 : 32;
-#define GO(BSS, GG)                                                                                                          \
-    do {                                                                                                                     \
-        if (B.diag_only) k_bsr_stream<BSS, GG, MODE, true, 2><<<B.nblk, kBlk, 0, c.stream>>>(B.blk_row.p, B.rowptr.p, B.col.p, B.val.p, x, y, ep, dot_partial); \
-        else if (B.ntb == 1) k_bsr_stream<BSS, GG, MODE, false, 1><<<B.nblk, kBlk, 0, c.stream>>>(B.blk_row.p, B.rowptr.p, B.col.p, B.val.p, x, y, ep, dot_partial); \
-        else k_bsr_stream<BSS, GG, MODE, false, 2><<<B.nblk, kBlk, 0, c.stream>>>(B.blk_row.p, B.rowptr.p, B.col.p, B.val.p, x, y, ep, dot_partial);          \
+    const bool fuse = x2 != nullptr && B.fused;
+#define GO(BSS, DG, PF, FS) k_bsr_stream<BSS, MODE, DG, PF, FS><<<B.nblk, kBlk, 0, c.stream>>>(B.blk_row.p, B.rowptr.p, FS ? B.f_col.p : B.col.p, \
+                                B.val.p, FS ? B.f_m.p : nullptr, x, x2, y, ep, dot_partial, G)
+#define GOB(BSS)                                                                                   \
+    do {                                                                                           \
+        if (fuse) { if (B.pref) GO(BSS, false, true, true); else GO(BSS, false, false, true); }     \
+        else if (B.diag_only) { if (B.pref) GO(BSS, true, true, false); else GO(BSS, true, false, false); } \
+        else { if (B.pref) GO(BSS, false, true, false); else GO(BSS, false, false, false); }        \
     } while (0)
-#define GOG(BSS) switch (G) { case 1: GO(BSS, 1); break; case 2: GO(BSS, 2); break; case 4: GO(BSS, 4); break; \
-                              case 8: GO(BSS, 8); break; case 16: GO(BSS, 16); break; default: GO(BSS, 32); break; }
-    if (B.bs == 3) { GOG(3) } else { GOG(2) }
-#undef GOG
+    if (B.bs == 3) GOB(3); else GOB(2);
+#undef GOB
 #undef GO
     PORO_LAUNCH_CHECK(c);
     return B.nblk;
 }
 
-template int bsr_launch<0>(Ctx&, const Bsr&, const double*, double*, const Epilogue&, double*);
-template int bsr_launch<1>(Ctx&, const Bsr&, const double*, double*, const Epilogue&, double*);
-template int bsr_launch<2>(Ctx&, const Bsr&, const double*, double*, const Epilogue&, double*);
-template int bsr_launch<3>(Ctx&, const Bsr&, const double*, double*, const Epilogue&, double*);
-template int bsr_launch<4>(Ctx&, const Bsr&, const double*, double*, const Epilogue&, double*);
+template int bsr_launch<0>(Ctx&, const Bsr&, const double*, double*, const Epilogue&, double*, const double*);
+template int bsr_launch<1>(Ctx&, const Bsr&, const double*, double*, const Epilogue&, double*, const double*);
+template int bsr_launch<2>(Ctx&, const Bsr&, const double*, double*, const Epilogue&, double*, const double*);
+template int bsr_launch<3>(Ctx&, const Bsr&, const double*, double*, const Epilogue&, double*, const double*);
+template int bsr_launch<4>(Ctx&, const Bsr&, const double*, double*, const Epilogue&, double*, const double*);
 
 }  // namespace poro

@@ -118,6 +118,7 @@ k_bsr_tma(const int4* __restrict__ desc, int nchunk, const int* __restrict__ crp
     if (tid == 0)
         for (int k = 0; k < kStages && k < nloc; ++k) issue(k);
 
+    const int lg = 31 - __clz(G);
     const int lane = tid & (G - 1);
     const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((tid & 31) & ~(G - 1)));
     double contrib = 0.0;
@@ -187,7 +188,7 @@ k_bsr_tma(const int4* __restrict__ desc, int nchunk, const int* __restrict__ crp
         // the stage is consumed: refill it with chunk k + kStages while rows are reduced and the epilogue runs
         if (tid == 0 && k + kStages < nloc) { fence_proxy_async(); issue(k + kStages); }
         // phase 2: G lanes per block row
-        for (int Rl = tid / G; Rl < nbr; Rl += kT / G) {
+        for (int Rl = tid >> lg; Rl < nbr; Rl += kT >> lg) {
             const int a = rpl[Rl], b = rpl[Rl + 1];
             double s[BS];
 #pragma unroll
@@ -318,7 +319,7 @@ bool bsr_build_tma(Ctx& c, Bsr& B, const std::vector<int>& rp) {
 // ---------------------------------------------------------------------------------------------
 // fused mass coupling: C (same block rows, diagonal blocks c M_IJ I with zeroed Dirichlet rows) rides along B
 // ---------------------------------------------------------------------------------------------
-bool bsr_fuse_coupling(Ctx& c, Bsr& B, const Csr& C) {
+bool bsr_fuse_coupling_tma(Ctx& c, Bsr& B, const Csr& C) {
     if (!B.t_ok || B.diag_only || C.nrows != B.nbrows * B.bs || C.ncols != B.nbcols * B.bs) return false;
     if ((int64_t)B.nbcols >= (1 << 29)) return false;
     const int BS = B.bs;

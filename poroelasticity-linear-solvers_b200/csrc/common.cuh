@@ -213,6 +213,10 @@ struct Bsr {
     DBuf<double> val;
     DBuf<int> blk_row;
     int nblk = 0;
+    bool pref = false;          // every chunk has <= 256 scalar rows: epilogue operands are prefetched (k_bsr_stream PREF)
+    bool fused = false;         // a mass coupling rides along (plain layout): one scalar per block + row mask in the column word
+    DBuf<double> f_m;
+    DBuf<int> f_col;
     // chunked layout of the TMA kernel (bsr_tma.cu); when present the plain val / col arrays above are released
     bool t_ok = false, t_fused = false;
     int t_nchunk = 0, t_cfg = 0;

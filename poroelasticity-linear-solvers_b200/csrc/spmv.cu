@@ -166,13 +166,13 @@ bool csr_fuse_coupling(Ctx& c, const Csr& A, const Csr& C) {
 }
 
 void spmv_fused(Ctx& c, const Csr& A, const double* x, const double* x2, double* y, SpmvMode mode, const double* z) {
-    PORO_REQUIRE(A.bsr_state == 1 && A.bsr->t_fused, "spmv_fused: no fused coupling on this matrix");
+    PORO_REQUIRE(A.bsr_state == 1 && (A.bsr->t_fused || A.bsr->fused), "spmv_fused: no fused coupling on this matrix");
     Epilogue ep{};
     ep.mode = mode;
     ep.z = z;
-    if (mode == SPMV_SET) bsr_tma_launch<SPMV_SET>(c, *A.bsr, x, y, ep, nullptr, x2);
-    else if (mode == SPMV_SUB) bsr_tma_launch<SPMV_SUB>(c, *A.bsr, x, y, ep, nullptr, x2);
-    else bsr_tma_launch<SPMV_ADD>(c, *A.bsr, x, y, ep, nullptr, x2);
+    if (mode == SPMV_SET) bsr_launch<SPMV_SET>(c, *A.bsr, x, y, ep, nullptr, x2);
+    else if (mode == SPMV_SUB) bsr_launch<SPMV_SUB>(c, *A.bsr, x, y, ep, nullptr, x2);
+    else bsr_launch<SPMV_ADD>(c, *A.bsr, x, y, ep, nullptr, x2);
 }
 
 static void try_bsr(Ctx& c, const Csr& A) {

@@ -51,6 +51,7 @@ bool bsr_fuse_coupling(Ctx& c, Bsr& B, const Csr& C);
 template <int MODE>
 int bsr_tma_launch(Ctx& c, const Bsr& B, const double* x, double* y, const Epilogue& ep, double* dot_partial, const double* x2 = nullptr);
 template <int MODE>
-int bsr_launch(Ctx& c, const Bsr& B, const double* x, double* y, const Epilogue& ep, double* dot_partial);
+int bsr_launch(Ctx& c, const Bsr& B, const double* x, double* y, const Epilogue& ep, double* dot_partial, const double* x2 = nullptr);
+bool bsr_fuse_coupling_tma(Ctx& c, Bsr& B, const Csr& C);
 
 }  // namespace poro
