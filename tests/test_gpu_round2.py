@@ -215,3 +215,28 @@ def test_field_convergence_test_stops_on_field_norms(gpu_ctx):
     r = sys_.b - sys_.A @ g["x"]
     normalize = max(np.linalg.norm(sys_.b[i]) for i in (sys_.is_s, sys_.is_f, sys_.is_p))
     assert max(np.abs(r[i]).max() for i in (sys_.is_s, sys_.is_f, sys_.is_p)) / normalize < 1e-6
+
+
+@pytest.mark.parametrize("block", ["s", "fp"])
+def test_single_block_drivers(gpu_ctx, block):
+    """solid.py / fluid-pressure.py (reference solid.py:111-180, fluid-pressure.py:85-136) -- the inner solver of
+    one block as a stand-alone KSP, against a direct solve of that block assembled on the host."""
+    import sys as _sys
+    _sys.path.insert(0, os.path.join(ROOT, "examples"))
+    from _single_block import DEFAULTS, build
+    from hostfem.problems import swelling
+    N = 5
+    ctx, cc, db, dx, host, rhs, keep = build(block, N, assemble="device", ctx=gpu_ctx, options_text=DEFAULTS[block])
+    cc.inner_solve(block, db, dx)
+    gpu_ctx.sync()
+    its, reason, rnorm = cc.inner_result(block)
+    ref, _ = swelling(3, N, "diagonal", {"ks": 1e6})
+    idx = ref.is_s if block == "s" else np.concatenate([ref.is_f, ref.is_p])
+    M = sp.csr_matrix(ref.A)[idx][:, idx].tocsc()
+    np.testing.assert_allclose(rhs, ref.b[idx], rtol=1e-12, atol=1e-14 * np.abs(ref.b).max())
+    xd = spla.spsolve(M, rhs)
+    assert reason > 0 and 0 < its < 200
+    x = dx.numpy()
+    assert np.linalg.norm(rhs - M @ x) / np.linalg.norm(rhs) <= 1e-7
+    assert rel(x, xd) <= 1e-5
+    gpu_ctx.set_halo(0, [], [0], [], [])
