@@ -61,10 +61,14 @@ __global__ void __launch_bounds__(kBlk, FUSE ? 3 : 4) k_bsr_stream(const int* __
 #pragma unroll
     for (int t = 0; t < kNtb; ++t) {
         const int i = threadIdx.x + t * kBlk;
-        c[t] = i < cnt ? __ldcs(col + p0 + i) : -1;
+        c[t] = -1;
         mk[t] = 0u;
         m[t] = 0.0;
-        if (FUSE && c[t] >= 0) { mk[t] = (unsigned)c[t] >> 29; c[t] &= 0x1fffffff; m[t] = __ldcs(mval + p0 + i); }
+        if (i < cnt) {
+            const int cw = __ldcs(col + p0 + i);          // FUSE: the top three bits carry the row mask (the word may be negative)
+            c[t] = FUSE ? (cw & 0x1fffffff) : cw;
+            if (FUSE) { mk[t] = (unsigned)cw >> 29; m[t] = __ldcs(mval + p0 + i); }
+        }
     }
     constexpr int NE = DIAG ? BS : BS * BS;     // stored entries per block
     double v[kNtb][NE];

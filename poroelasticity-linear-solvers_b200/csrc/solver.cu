@@ -76,7 +76,26 @@ PCJacobi::PCJacobi(Ctx* c, const Csr& A) : ctx(c) {
     PORO_CUDA(cudaMemcpy(dinv.p, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
 }
 
-PCDense::PCDense(Ctx* c, const Csr& A) : ctx(c), n(A.nrows) { dense_inverse(*c, A, inv); }
+PCDense::PCDense(Ctx* c, const Csr& A_) : ctx(c), n(A_.nrows) {
+    dense_inverse(*c, A_, inv);
+    refine = c->opt_i("-poro_dense_refine", 1);
+    if (refine > 0) {
+        csr_copy(*c, A_, A);
+        csr_choose_lanes(A);
+        r.alloc((size_t)n);
+        d.alloc((size_t)n);
+        PORO_CUDA(cudaStreamSynchronize(c->stream));
+    }
+}
+
+void PCDense::apply(const double* x, double* y) {
+    dense_gemv(*ctx, inv.p, n, x, y);
+    for (int it = 0; it < refine; ++it) {
+        spmv(*ctx, A, y, r.p, SPMV_SUB, x);          // r = x - A y
+        dense_gemv(*ctx, inv.p, n, r.p, d.p);
+        vec_axpy(*ctx, y, 1.0, d.p, n);
+    }
+}
 
 // rigid-body modes from dof coordinates (host), node-blocked dofs; mirrors oracle/amg.py
 static void rigid_body_modes(const double* coords, int64_t ndof, int dim, std::vector<double>& B, int& k) {

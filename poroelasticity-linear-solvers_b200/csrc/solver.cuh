@@ -76,8 +76,11 @@ struct PCJacobi : PC {
 
 struct PCDense : PC {   // exact block solve: explicit inverse (stands in for MUMPS `preonly + lu` on small blocks)
     Ctx* ctx; DBuf<double> inv; int n;
+    // one step of iterative refinement with the sparse block (y += inv (x - A y)): the Gauss-Jordan inverse of the
+    // ill-conditioned `undrained` blocks (k_s = 1e6) alone is only good to ~1e-6 against a sparse LU
+    Csr A; DBuf<double> r, d; int refine = 1;
     PCDense(Ctx* c, const Csr& A);
-    void apply(const double* x, double* y) override { dense_gemv(*ctx, inv.p, n, x, y); }
+    void apply(const double* x, double* y) override;
     const char* kind() const override { return "lu(dense)"; }
 };
 

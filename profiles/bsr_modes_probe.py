@@ -25,8 +25,9 @@ if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 MODES = {0: ("y = A x", 16), 1: ("y = z - A x", 24), 2: ("y = z + A x", 24), 3: ("Chebyshev step", 64), 4: ("w = A p, p.w", 24)}
 out = {"N": N, "n": n, "nnzb": int(nnzb), "peak": peak, "rows": []}
-VARIANTS = [("ld.global.cs (bsr.cu)", {"-poro_bsr_tma": 0}), ("TMA 512x2, 2 CTA/SM", {"-poro_bsr_tma_cfg": 0}),
-            ("TMA 256x2, 4 CTA/SM", {"-poro_bsr_tma_cfg": 1}), ("TMA 256x3, 3 CTA/SM", {"-poro_bsr_tma_cfg": 2})]
+VARIANTS = [("ld.global.cs (bsr.cu)", {"-poro_bsr_tma": 0}), ("TMA 512x2, 2 CTA/SM", {"-poro_bsr_tma": 1, "-poro_bsr_tma_cfg": 0}),
+            ("TMA 256x2, 4 CTA/SM", {"-poro_bsr_tma": 1, "-poro_bsr_tma_cfg": 1}), ("TMA 256x3, 3 CTA/SM", {"-poro_bsr_tma": 1, "-poro_bsr_tma_cfg": 2}),
+            ("ld.global.cs, no operand prefetch", {"-poro_bsr_tma": 0, "-poro_bsr_prefetch": 0})]
 if os.environ.get("PROBE_VARIANTS"):
     VARIANTS = [VARIANTS[int(i)] for i in os.environ["PROBE_VARIANTS"].split(",")]
 if os.environ.get("PROBE_MODES"):
