@@ -57,7 +57,8 @@ BENCH_OPTIONS = """
 """
 PHASE_NAMES = {0: "outer_A_apply", 1: "pc_apply", 2: "s_solve", 3: "fp_split0(f)", 4: "fp_split1(p)", 5: "gram_schmidt",
                6: "fp_coupling", **{8 + l: "s_amg_L%d" % l for l in range(8)}, **{16 + l: "f_amg_L%d" % l for l in range(8)},
-               **{24 + l: "p_amg_L%d" % l for l in range(8)}, 32: "A_remainder_csr", 33: "A_ss", 34: "A_sf", 35: "A_fs", 36: "A_ff"}
+               **{24 + l: "p_amg_L%d" % l for l in range(8)}, 32: "A_remainder_csr", 33: "A_part0", 34: "A_part1", 35: "A_part2", 36: "A_part3",
+               37: "s_L0_cheby_step_launch"}
 RTOL = 1e-8
 METRIC = "3D swelling (swelling-3d.py) solve to rtol 1e-8: DoFs solved per second (n_dofs / time-to-1e-8)"
 UNIT = "DoF/s"
@@ -418,15 +419,23 @@ def main():
         return
     peak, peak_src = peaks()
     achieved = (op_bytes / 1e9) / (op_ms / 1e3 / max(op_calls, 1)) if op_calls else None
-    # dominant kernel: the BSR stream kernel.  Its launch inside the outer operator (slot 33 = first node-blocked part) is
-    # timed live by CUDA events on the library's stream during the profiled solves.
+    # dominant kernel: the Chebyshev-step launch of the BSR kernel on P_ss (level 0 of the solid V-cycle) -- the launch with
+    # the largest share of a solve (ncu launch list in profiles/).  It is timed live by CUDA events on the library's stream
+    # around every such launch of the profiled solves (slot 37); bytes = one product with P_ss in its launched format plus
+    # the epilogue's vector traffic (r, d, D^-1, x read; r, d, x written: 56 B per row).
     parts = ksp.parts_info()
     FORMATS = {0: "CSR", 1: "BSR3", 2: "diag-BSR3", 3: "fused BSR3 + mass coupling"}
     dom = None
-    if len(parts) > 1 and 33 in phases and phases[33][1] > 0:
-        ms33, n33 = phases[33]
-        dom = {"bytes": parts[1][0], "format": FORMATS.get(parts[1][1], "?"), "avg_ms": ms33 / n33, "launches": n33,
-               "achieved": parts[1][0] / 1e9 / (ms33 / n33 / 1e3)}
+    try:
+        ss_bytes, ss_fmt = pc.getPythonContext().block_bytes("ss")
+        ns_rows = pc.getPythonContext().block_info("ss")[0]
+        if 37 in phases and phases[37][1] > 0:
+            ms37, n37 = phases[37]
+            nbytes = ss_bytes + 56 * ns_rows
+            dom = {"bytes": nbytes, "format": FORMATS.get(ss_fmt, "?"), "avg_ms": ms37 / n37, "launches": n37,
+                   "achieved": nbytes / 1e9 / (ms37 / n37 / 1e3)}
+    except Exception as e:
+        print("[bench] dominant-kernel profile unavailable: %r" % (e,), file=sys.stderr)
     stats = pc.getPythonContext().stats()
     # value: device time (CUDA events); e2e: host wall clock around the K host-buffer calls (what a caller observes)
     t_solve, t_solve_e = dt / args.steps, max(dt_e, wall["e2e"]) / args.steps
@@ -453,8 +462,9 @@ def main():
     if extra:
         line["config"]["extra_options"] = extra
     if dom:
-        traffic, traffic_src = measured_traffic("outer_part0", dom["bytes"])
-        line["roofline"] = {"bound": "hbm", "kernel": "first node-blocked launch of the outer operator product (%s, rows of the solid field)" % dom["format"],
+        traffic, traffic_src = measured_traffic("s_L0_cheby_step", dom["bytes"])
+        line["roofline"] = {"bound": "hbm", "kernel": "k_bsr_stream<3, mode 3 (Chebyshev step), PREF> on P_ss (%s), level 0 of the solid V-cycle: "
+                                                      "the launch with the largest share of the solve" % dom["format"],
                             "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["achieved"] / peak,
                             "traffic": traffic, "traffic_source": traffic_src,
                             "peak_source": peak_src, "bytes_per_launch": dom["bytes"], "format": dom["format"],

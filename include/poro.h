@@ -157,6 +157,9 @@ int poro_aar_destroy(poro_aar* aar);
 /* ---- micro-benchmark / introspection entry points ----------------------------------------- */
 /* block names: "A" (whole permuted operator), "ss","sf","sp","fs","ff","fp","ps","pf","pp" of P */
 int poro_pc_block_info(poro_pc* pc, const char* name, int64_t* nrows, int64_t* ncols, int64_t* nnz);
+/* algorithmic bytes of one product y = B x with a block in the format it is launched in (0 CSR, 1 BSR, 2 diagonal BSR):
+ * 12 nnz + 4 (nrows+1) + 8 nrows + 8 ncols, or (8 BS^2 + 4) nnzb + 4 (nbrows+1) + 8 nrows + 8 ncols */
+int poro_pc_block_bytes(poro_pc* pc, const char* name, int64_t* bytes, int* format);
 /* copy a block to host CSR arrays sized from poro_pc_block_info (tests: createSubMatrix parity) */
 int poro_pc_block_copy(poro_pc* pc, const char* name, int64_t* rowptr, int32_t* col, double* val);
 /* one application of the inner solver of a block: "s","f","p","fp","diff" (z = K \ r) */
@@ -176,7 +179,8 @@ int poro_ksp_profile(poro_ksp* ksp, int enable, double* op_ms, int64_t* op_calls
 int poro_ksp_parts_info(poro_ksp* ksp, int64_t* bytes, int* format, int cap, int* n);
 /* phase profile (CUDA events on the launching stream): slots 0 outer operator, 1 preconditioner apply,
  * 2 solid solve, 3 fp split 0, 4 fp split 1, 5 orthogonalisation, 6 fp coupling product,
- * 8+l / 16+l / 24+l AMG level l (inclusive) of the s / f / p hierarchies.  enable as in poro_ksp_profile. */
+ * 8+l / 16+l / 24+l AMG level l (inclusive) of the s / f / p hierarchies, 32.. the launches of the outer operator,
+ * 37 the level-0 Chebyshev-step launch of the solid hierarchy.  enable as in poro_ksp_profile. */
 int poro_profile(poro_ctx* ctx, int enable, double* ms, int64_t* calls, int n);
 /* operator y = A x in the solver's internal (field-major) ordering incl. halo exchange */
 int poro_ksp_mult(poro_ksp* ksp, const double* x_dev, double* y_dev);

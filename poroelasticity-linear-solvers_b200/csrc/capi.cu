@@ -730,6 +730,25 @@ int poro_pc_block_info(poro_pc* pc, const char* name, int64_t* nrows, int64_t* n
     API_END
 }
 
+// algorithmic bytes of ONE plain product y = B x with a block in the format it is launched in (0 CSR, 1 BSR, 2 diagonal BSR)
+int poro_pc_block_bytes(poro_pc* pc, const char* name, int64_t* bytes, int* format) {
+    API_BEGIN
+    MatOp* m = find_block(pc, name);
+    if (!m) throw Error(std::string("no such block: ") + name);
+    const Csr& B = m->mat();
+    csr_ensure_bsr(pc->ctx->c, B);
+    if (B.bsr_state == 1) {
+        const Bsr& b = *B.bsr;
+        const int64_t ne = b.diag_only ? b.bs : b.bs * b.bs;
+        *bytes = (8 * ne + 4) * b.nnzb + 4 * ((int64_t)b.nbrows + 1) + 8 * (int64_t)B.nrows + 8 * (int64_t)B.ncols;
+        *format = b.diag_only ? 2 : 1;
+    } else {
+        *bytes = 12 * B.nnz + 4 * ((int64_t)B.nrows + 1) + 8 * (int64_t)B.nrows + 8 * (int64_t)B.ncols;
+        *format = 0;
+    }
+    API_END
+}
+
 int poro_pc_block_copy(poro_pc* pc, const char* name, int64_t* rowptr, int32_t* col, double* val) {
     API_BEGIN
     MatOp* m = find_block(pc, name);

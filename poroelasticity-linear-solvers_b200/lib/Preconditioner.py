@@ -73,6 +73,12 @@ class PreconditionerCC(object):
         _capi.check(self.ctx.lib.poro_pc_block_info(self.h, name.encode(), C.byref(r), C.byref(c), C.byref(z)))
         return r.value, c.value, z.value
 
+    def block_bytes(self, name):
+        """(algorithmic bytes of one product with the block, format 0 CSR / 1 BSR / 2 diagonal BSR)."""
+        b, f = C.c_int64(), C.c_int()
+        _capi.check(self.ctx.lib.poro_pc_block_bytes(self.h, name.encode(), C.byref(b), C.byref(f)))
+        return b.value, f.value
+
     def block(self, name):
         """Copy of a device block as scipy CSR (blocks: ss sf sp ff fp pp fps fpfp schur diff)."""
         import scipy.sparse as sp

@@ -1,4 +1,4 @@
-// Host harness for csrc/next/gen_stencil.cuh: runs the __host__ __device__ row logic of the device-side matrix
+// Host harness for csrc/gen_stencil.cuh: runs the __host__ __device__ row logic of the device-side matrix
 // generator over all rows on the CPU (g++), for tests/test_gen_stencil_host.py.
 #include <stdint.h>
 

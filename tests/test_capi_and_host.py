@@ -97,23 +97,3 @@ def test_shipped_option_files_parse_and_match_bench():
         assert len(opts) >= 10 and all(k.startswith("-") for k, _ in opts)
     shipped = dict(parse_petsc_options(open(os.path.join(ROOT, "options", "petsc-options-b200")).read()))
     assert shipped == dict(parse_petsc_options(bench.BENCH_OPTIONS))
-
-
-def test_next_sources_build(tmp_path):
-    """csrc/next holds round-2 work in progress that is not linked into libporo.so; it must at least build for sm_100a."""
-    import glob
-    import shutil
-    import subprocess
-    if shutil.which("nvcc") is None:
-        pytest.skip("nvcc not available")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    srcs = sorted(glob.glob(os.path.join(root, "poroelasticity-linear-solvers_b200", "csrc", "next", "*.cu")))
-    assert srcs
-    for s in srcs:
-        out = str(tmp_path / (os.path.basename(s) + ".o"))
-        subprocess.run(["nvcc", "-O1", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "--extended-lambda",
-                        "-c", s, "-o", out], check=True)
-        assert os.path.getsize(out) > 0
-    # and none of it is part of the shipped library
-    build_py = open(os.path.join(root, "poroelasticity-linear-solvers_b200", "build.py")).read()
-    assert "next/" not in build_py

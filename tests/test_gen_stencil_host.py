@@ -1,5 +1,6 @@
-"""The row logic of the device-side matrix generator (csrc/next/gen_stencil.cuh, __host__ __device__) run on the
-CPU through a g++ harness, against hostfem/stencil.py and the element assembler; plus an nvcc build of the kernels."""
+"""The row logic of the device-side matrix generator (csrc/gen_stencil.cuh, __host__ __device__; used by csrc/gen.cu) run
+on the CPU through a g++ harness, against hostfem/stencil.py and the element assembler.  The kernels themselves are tested on
+the GPU in tests/test_generator.py."""
 import ctypes as C
 import os
 import shutil
@@ -12,7 +13,7 @@ import scipy.sparse as sp
 from hostfem import problems, stencil
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-NEXT = os.path.join(ROOT, "poroelasticity-linear-solvers_b200", "csrc", "next")
+NEXT = os.path.join(ROOT, "poroelasticity-linear-solvers_b200", "csrc")
 SHAPE = {"22": (2, 2), "21": (2, 1), "12": (1, 2), "11": (1, 1)}
 
 
@@ -77,11 +78,3 @@ def test_dirichlet_rows_and_node_ranges(harness):
         part = _generate(harness, gen, K, kr, kc, br, bc, int(key[0] == key[1]), masks[key[0]], (a, b)).tocsr()
         part.eliminate_zeros()
         assert abs(part - want[a * br: b * br]).max() <= 1e-14 * max(abs(want).max(), 1e-300)
-
-
-@pytest.mark.skipif(shutil.which("nvcc") is None, reason="nvcc not available")
-def test_kernels_build_for_sm100a(tmp_path):
-    out = str(tmp_path / "gen_stencil.o")
-    subprocess.run(["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-c",
-                    os.path.join(NEXT, "gen_stencil.cu"), "-o", out], check=True)
-    assert os.path.getsize(out) > 0
