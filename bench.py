@@ -45,6 +45,8 @@ BENCH_OPTIONS = """
 -s_ksp_type preonly
 -s_pc_type hypre
 -s_pc_amg_theta 0.04
+-s_pc_amg_coarse_size 6000
+-poro_amg_dense_limit 8192
 -fp_ksp_type preonly
 -fp_pc_fieldsplit_type schur
 -fp_pc_fieldsplit_schur_fact_type lower
@@ -54,6 +56,7 @@ BENCH_OPTIONS = """
 -fp_fieldsplit_0_pc_type chebyshev
 -fp_fieldsplit_1_ksp_type preonly
 -fp_fieldsplit_1_pc_type hypre
+-fp_fieldsplit_1_pc_amg_coarse_size 6000
 """
 PHASE_NAMES = {0: "outer_A_apply", 1: "pc_apply", 2: "s_solve", 3: "fp_split0(f)", 4: "fp_split1(p)", 5: "gram_schmidt",
                6: "fp_coupling", **{8 + l: "s_amg_L%d" % l for l in range(8)}, **{16 + l: "f_amg_L%d" % l for l in range(8)},
@@ -126,9 +129,10 @@ def oracle_solver(sys_, par, max_it):
     from oracle import cport
     dim = sys_.dim
     B = rigid_body_modes(sys_.coords_s, dim)
-    amg_s = lambda M: SAAMG(M, dim, B, theta=0.04)                              # -s_pc_amg_theta 0.04
+    # coarsening stops below 6 000 (global) rows, where one dense inverse is cheaper than further latency-bound levels
+    amg_s = lambda M: SAAMG(M, dim, B, theta=0.04, coarse_size=6000, dense_limit=8192)   # -s_pc_amg_theta 0.04 -s_pc_amg_coarse_size 6000
     cheb_f = lambda M: SAAMG(M, dim, B, max_levels=1, cheby_degree=4, dense_limit=0)   # -fp_fieldsplit_0_pc_type chebyshev
-    amg_p = lambda M: SAAMG(M, 1, None)
+    amg_p = lambda M: SAAMG(M, 1, None, coarse_size=6000, dense_limit=8192)
     mkfp = lambda M: SchurLower(M, sys_.nf, sys_.np_, krylov_solver("preonly", cheb_f), krylov_solver("preonly", amg_p), "f")
     pc = BlockPC(sys_, {"s": krylov_solver("preonly", amg_s), "fp": mkfp})
     A = sys_.A
