@@ -123,6 +123,7 @@ struct Ctx {
     void* comm = nullptr;
     NcclApi* nccl = nullptr;
     struct P2PState* p2p = nullptr;   // receive arena + mapped peer arenas (dist.cu)
+    bool p2p_fused = true;            // one kernel per exchange (push + wait + copy) instead of two
     std::map<std::string, std::string> opts;
     double* h_pin = nullptr;     // pinned host scratch for scalar read-back
     double* d_scal = nullptr;    // device scratch for reductions

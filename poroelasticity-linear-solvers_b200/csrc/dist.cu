@@ -93,8 +93,11 @@ void dist_finalize(Ctx& c) {
     c.comm = nullptr;
 }
 
+static bool p2p_allreduce(Ctx& c, double* d_vals, int k);
+
 void dist_allreduce_sum(Ctx& c, double* d_vals, int k) {
     if (c.nranks <= 1) return;
+    if (p2p_allreduce(c, d_vals, k)) return;
     NCCL_OK(c.nccl, c.nccl->AllReduce(d_vals, d_vals, (size_t)k, NCCL_FLOAT64, NCCL_SUM, (ncclComm_p)c.comm, c.stream));
 }
 
@@ -128,7 +131,19 @@ struct P2PState {
     size_t bytes = 0, used = 0;
     std::vector<unsigned char*> peer;          // mapped arenas of the other ranks (nullptr for self)
     static constexpr size_t kFlagBytes = 1 << 16;   // head of the arena: 16 Ki sequence flags
-    int flags_used = 0;
+    int flags_used = 16;                            // flags 0..15: small all-reduce, indexed by source rank
+    // small all-reduce over peer stores: one region per source rank (2 parities x kArMax doubles) right after the flags
+    static constexpr int kArMax = 8192;
+    static constexpr size_t kArRegion = (size_t)2 * kArMax * sizeof(double);
+    uint32_t* ar_state = nullptr;                   // device: [seq]
+};
+
+struct P2PArArgs {
+    double* peer_region[8];      // where this rank writes in every other rank's arena (nullptr for self)
+    uint32_t* peer_flag[8];
+    const double* my_region[8];  // region of source rank r in this rank's arena
+    const uint32_t* my_flag[8];
+    int nranks, me;
 };
 
 static void p2p_finalize(Ctx& c) {
@@ -176,8 +191,13 @@ static void p2p_init(Ctx& c) {
         if (c.has_opt("-poro_verbose") && c.rank == 0) fprintf(stderr, "  [dist] peer-to-peer halo path unavailable: NCCL send/recv is used\n");
         return;
     }
-    st->used = P2PState::kFlagBytes;
+    st->used = P2PState::kFlagBytes + (size_t)c.nranks * P2PState::kArRegion;
+    if (c.nranks <= 8 && c.opt_i("-poro_p2p_allreduce", 1)) {
+        PORO_CUDA(cudaMalloc(&st->ar_state, sizeof(uint32_t)));
+        PORO_CUDA(cudaMemset(st->ar_state, 0, sizeof(uint32_t)));
+    }
     c.p2p = st.release();
+    c.p2p_fused = c.opt_i("-poro_p2p_fused", 1) != 0;
     if (c.has_opt("-poro_verbose") && c.rank == 0) fprintf(stderr, "  [dist] peer-to-peer halo path: %zu MB arena per rank, %d peers mapped\n", c.p2p->bytes >> 20, c.nranks - 1);
 }
 
@@ -288,13 +308,107 @@ __global__ void __launch_bounds__(256) k_p2p_wait_copy(P2PArgs a, double* __rest
     }
 }
 
+// push, wait and copy in ONE launch: every CTA first stores its share of the boundary values into the neighbours' regions,
+// the last one to finish releases the flags; then every CTA waits for the incoming flags and copies its share of the
+// received values.  The CTAs only wait for REMOTE events, and the grid (<= 2 CTAs per SM) is always co-resident, so the
+// pushes a neighbour waits for can never be stuck behind spinning CTAs.
+__global__ void __launch_bounds__(256) k_p2p_exchange(P2PArgs a, const double* __restrict__ x, const int* __restrict__ send_idx,
+                                                      int nsend, double* __restrict__ ghost, int nrecv, uint32_t* __restrict__ state) {
+    const uint32_t seq = state[0] + 1u;
+    const int par = (int)(seq & 1u);
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < nsend; i += gridDim.x * 256) {
+        int k = 0;
+        while (k + 1 < a.nn && i >= a.nb[k].send_end) ++k;
+        a.nb[k].peer_data[par][i - a.nb[k].send_begin] = x[send_idx[i]];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(&state[2], 1u);
+        if (t == gridDim.x - 1) {
+            __threadfence_system();
+            for (int k = 0; k < a.nn; ++k)
+                if (a.nb[k].send_end > a.nb[k].send_begin) st_release_sys(a.nb[k].peer_flag, seq);
+        }
+    }
+    if (threadIdx.x < a.nn) {
+        const P2PNeighDev& d = a.nb[threadIdx.x];
+        if (d.recv_end > d.recv_begin)
+            while ((int32_t)(ld_acquire_sys(d.my_flag) - seq) < 0) { }
+    }
+    __syncthreads();
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < nrecv; i += gridDim.x * 256) {
+        int k = 0;
+        while (k + 1 < a.nn && i >= a.nb[k].recv_end) ++k;
+        ghost[i] = __ldcv(a.nb[k].my_data[par] + (i - a.nb[k].recv_begin));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(&state[3], 1u);
+        if (t == gridDim.x - 1) { state[2] = 0u; state[3] = 0u; state[0] = seq; state[1] = seq; }
+    }
+}
+
 void p2p_exchange(Ctx& c, P2PSlots& s, const int* send_idx, const double* x_owned, double* ghost_out) {
+    if (c.p2p_fused) {
+        const int n = std::max(s.nsend, s.nrecv);
+        const int g = std::max(1, std::min((n + 255) / 256, c.sm_count * 2));
+        k_p2p_exchange<<<g, 256, 0, c.stream>>>(s.args, x_owned, send_idx, s.nsend, ghost_out, s.nrecv, s.d_state);
+        PORO_LAUNCH_CHECK(c);
+        return;
+    }
     const int gs = std::max(1, std::min((s.nsend + 255) / 256, c.sm_count * 2));
     const int gr = std::max(1, std::min((s.nrecv + 255) / 256, c.sm_count * 2));
     k_p2p_push<<<gs, 256, 0, c.stream>>>(s.args, x_owned, send_idx, s.nsend, s.d_state);
     PORO_LAUNCH_CHECK(c);
     k_p2p_wait_copy<<<gr, 256, 0, c.stream>>>(s.args, ghost_out, s.nrecv, s.d_state);
     PORO_LAUNCH_CHECK(c);
+}
+
+// sum of k <= 8192 doubles over all ranks by peer stores: every rank writes its values into its region of every other
+// rank's arena and releases a flag there; after all flags have arrived the values are added in RANK ORDER, so every rank
+// gets bit-identical sums.  One single-CTA kernel, no NCCL: the per-iteration reductions of GMRES / CG and the gathered
+// coarse right-hand sides are a few hundred bytes and purely latency-bound.
+__global__ void __launch_bounds__(256) k_p2p_allreduce(P2PArArgs a, double* __restrict__ vals, int k, uint32_t* __restrict__ state) {
+    const uint32_t seq = *state + 1u;
+    const size_t par_off = (size_t)(seq & 1u) * P2PState::kArMax;
+    for (int r = 0; r < a.nranks; ++r) {
+        if (r == a.me) continue;
+        double* dst = a.peer_region[r] + par_off;
+        for (int i = threadIdx.x; i < k; i += 256) dst[i] = vals[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < a.nranks && threadIdx.x != a.me) {
+        st_release_sys(a.peer_flag[threadIdx.x], seq);
+        while ((int32_t)(ld_acquire_sys(a.my_flag[threadIdx.x]) - seq) < 0) { }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < k; i += 256) {
+        double s = 0.0;
+        for (int r = 0; r < a.nranks; ++r) s += r == a.me ? vals[i] : __ldcv(a.my_region[r] + par_off + i);
+        vals[i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *state = seq;
+}
+
+static bool p2p_allreduce(Ctx& c, double* d_vals, int k) {
+    if (!c.p2p || !c.p2p->ar_state || k > P2PState::kArMax) return false;
+    P2PState& st = *c.p2p;
+    P2PArArgs a{};
+    a.nranks = c.nranks;
+    a.me = c.rank;
+    for (int r = 0; r < c.nranks; ++r) {
+        // region of source rank `src` in an arena: flags first, then the regions in source-rank order (same layout everywhere)
+        a.my_region[r] = (const double*)(st.arena + P2PState::kFlagBytes + (size_t)r * P2PState::kArRegion);
+        a.my_flag[r] = (const uint32_t*)st.arena + r;
+        a.peer_region[r] = r == c.rank ? nullptr : (double*)(st.peer[r] + P2PState::kFlagBytes + (size_t)c.rank * P2PState::kArRegion);
+        a.peer_flag[r] = r == c.rank ? nullptr : (uint32_t*)st.peer[r] + c.rank;
+    }
+    k_p2p_allreduce<<<1, 256, 0, c.stream>>>(a, d_vals, k, st.ar_state);
+    PORO_LAUNCH_CHECK(c);
+    return true;
 }
 
 // ---- set-up primitives of the distributed hierarchy (distamg.cu): grouped byte send/recv, all-gather of int64 --------
