@@ -29,7 +29,7 @@ static constexpr int kMaxBRows = 256;     // block rows per chunk (row pointers 
 // FUSE: a mass coupling c M (x) I with the same block pattern rides along (one scalar per block in `mval`, a 3-bit row mask
 //       in the top bits of the column word): y = A x + C x2 in one pass.
 template <int BS, int MODE, bool DIAG, bool PREF, bool FUSE>
-__global__ void __launch_bounds__(kBlk, FUSE ? 3 : 4) k_bsr_stream(const int* __restrict__ blk_row, const int* __restrict__ rowptr,
+__global__ void __launch_bounds__(kBlk, FUSE ? 3 : 4) k_bsr_stream(const int4* __restrict__ desc, const int* __restrict__ rowptr,
                                                      const int* __restrict__ col, const double* __restrict__ val,
                                                      const double* __restrict__ mval, const double* __restrict__ x,
                                                      const double* __restrict__ x2, double* __restrict__ y, Epilogue ep,
@@ -39,8 +39,10 @@ __global__ void __launch_bounds__(kBlk, FUSE ? 3 : 4) k_bsr_stream(const int* __
     __shared__ double rsum[kMaxBRows * BS];
     __shared__ int rp[kMaxBRows + 1];
     __shared__ double red[kBlk / 32];
-    const int R0 = blk_row[blockIdx.x], R1 = blk_row[blockIdx.x + 1];
-    const int nbr = R1 - R0;
+    // one 16-byte descriptor per chunk {first block row, block rows, first block, blocks}: the matrix loads below depend on
+    // nothing else (the row pointers are only needed for the reduction and are fetched behind them)
+    const int4 dsc = __ldg(desc + blockIdx.x);
+    const int R0 = dsc.x, nbr = dsc.y, p0 = dsc.z, cnt = dsc.w;
     // epilogue operands of this thread's row, requested before anything else
     const bool has_row = PREF && (int)threadIdx.x < nbr * BS;
     const int myrow = R0 * BS + threadIdx.x;
@@ -50,10 +52,6 @@ __global__ void __launch_bounds__(kBlk, FUSE ? 3 : 4) k_bsr_stream(const int* __
         else if (MODE == 3) { e0 = ep.r[myrow]; e1 = ep.d_old[myrow]; e2 = ep.dinv[myrow]; e3 = ep.xv[myrow]; }
         else if (MODE == 4) e0 = x[myrow];
     }
-    for (int i = threadIdx.x; i <= nbr; i += kBlk) rp[i] = rowptr[R0 + i];
-    __syncthreads();
-    const int p0 = rp[0];
-    const int cnt = rp[nbr] - p0;
     // phase 1: one thread per block
     int c[kNtb];
     unsigned mk[kNtb];
@@ -79,6 +77,7 @@ __global__ void __launch_bounds__(kBlk, FUSE ? 3 : 4) k_bsr_stream(const int* __
 #pragma unroll
         for (int e = 0; e < NE; ++e) v[t][e] = c[t] >= 0 ? __ldcs(vb + e * 32) : 0.0;
     }
+    for (int i = threadIdx.x; i <= nbr; i += kBlk) rp[i] = rowptr[R0 + i];     // needed after the barrier only
 #pragma unroll
     for (int t = 0; t < kNtb; ++t) {
         const int i = threadIdx.x + t * kBlk;
@@ -260,6 +259,18 @@ bool bsr_from_csr(Ctx& c, const Csr& A, int BS, Bsr& out, double max_fill) {
     out.nblk = (int)blk.size() - 1;
     out.blk_row.alloc(blk.size());
     PORO_CUDA(cudaMemcpyAsync(out.blk_row.p, blk.data(), blk.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+    {
+        std::vector<int> dsc((size_t)out.nblk * 4);
+        for (int b = 0; b < out.nblk; ++b) {
+            dsc[4 * b] = blk[b];
+            dsc[4 * b + 1] = blk[b + 1] - blk[b];
+            dsc[4 * b + 2] = rp[blk[b]];
+            dsc[4 * b + 3] = rp[blk[b + 1]] - rp[blk[b]];
+        }
+        out.blk_desc.alloc(dsc.size());
+        PORO_CUDA(cudaMemcpyAsync(out.blk_desc.p, dsc.data(), dsc.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+        PORO_CUDA(cudaStreamSynchronize(c.stream));
+    }
     PORO_CUDA(cudaStreamSynchronize(c.stream));
     // Blackwell path: chunked layout for the persistent TMA kernel; the plain arrays are only kept when it is unavailable
     if (c.opt_i("-poro_bsr_tma", 0) && bsr_build_tma(c, out, rp)) {
@@ -331,7 +342,7 @@ int bsr_launch(Ctx& c, const Bsr& B, const double* x, double* y, const Epilogue&
     const double a = B.nbrows ? (double)B.nnzb / B.nbrows : 0.0;
     const int G = a <= 1.5 ? 1 : a <= 4 ? 2 : a <= 12 ? 4 : a <= 48 ? 8 : a <= 160 ? 16 : 32;
     const bool fuse = x2 != nullptr && B.fused;
-#define GO(BSS, DG, PF, FS) k_bsr_stream<BSS, MODE, DG, PF, FS><<<B.nblk, kBlk, 0, c.stream>>>(B.blk_row.p, B.rowptr.p, FS ? B.f_col.p : B.col.p, \
+#define GO(BSS, DG, PF, FS) k_bsr_stream<BSS, MODE, DG, PF, FS><<<B.nblk, kBlk, 0, c.stream>>>(reinterpret_cast<const int4*>(B.blk_desc.p), B.rowptr.p, FS ? B.f_col.p : B.col.p, \
                                 B.val.p, FS ? B.f_m.p : nullptr, x, x2, y, ep, dot_partial, G)
 #define GOB(BSS)                                                                                   \
     do {                                                                                           \

@@ -212,7 +212,7 @@ struct Bsr {
     bool diag_only = false;     // blocks are diagonal (e.g. M (x) I couplings): BS values per block instead of BS^2
     DBuf<int> rowptr, col;
     DBuf<double> val;
-    DBuf<int> blk_row;
+    DBuf<int> blk_row, blk_desc;    // chunk boundaries; per chunk {first block row, block rows, first block, blocks}
     int nblk = 0;
     bool pref = false;          // every chunk has <= 256 scalar rows: epilogue operands are prefetched (k_bsr_stream PREF)
     bool fused = false;         // a mass coupling rides along (plain layout): one scalar per block + row mask in the column word

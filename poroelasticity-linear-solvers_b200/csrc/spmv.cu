@@ -29,7 +29,7 @@ static constexpr int kMaxRows = 1024;               // rows per row block (row p
 // CSR stream
 // ---------------------------------------------------------------------------------------------
 template <int G, int MODE>
-__global__ void __launch_bounds__(kSpmvBlock) k_spmv_stream(const int* __restrict__ blk_row, const int* __restrict__ rowptr,
+__global__ void __launch_bounds__(kSpmvBlock) k_spmv_stream(const int4* __restrict__ desc, const int* __restrict__ rowptr,
                                                             const int* __restrict__ col, const double* __restrict__ val,
                                                             const double* __restrict__ x, double* __restrict__ y, Epilogue ep,
                                                             double* __restrict__ dot_partial) {
@@ -37,13 +37,9 @@ __global__ void __launch_bounds__(kSpmvBlock) k_spmv_stream(const int* __restric
     __shared__ double rsum[kMaxRows];
     __shared__ int rp[kMaxRows + 1];
     __shared__ double red[kSpmvBlock / 32];
-    const int r0 = blk_row[blockIdx.x], r1 = blk_row[blockIdx.x + 1];
-    const int nr = r1 - r0;
-    // the block's slice of the row pointer, coalesced, once
-    for (int i = threadIdx.x; i <= nr; i += kSpmvBlock) rp[i] = rowptr[r0 + i];
-    __syncthreads();
-    const int p0 = rp[0];
-    const int cnt = rp[nr] - p0;
+    // one 16-byte descriptor per row block {first row, rows, first nonzero, nonzeros}: the matrix loads depend on nothing else
+    const int4 dsc = __ldg(desc + blockIdx.x);
+    const int r0 = dsc.x, nr = dsc.y, p0 = dsc.z, cnt = dsc.w;
     const int* __restrict__ cb = col + p0;
     const double* __restrict__ vb = val + p0;
     // phase 1: stream the block's nonzeros; all matrix loads are issued before the first gather
@@ -55,6 +51,8 @@ __global__ void __launch_bounds__(kSpmvBlock) k_spmv_stream(const int* __restric
         cidx[t] = i < cnt ? __ldcs(cb + i) : -1;
         v[t] = i < cnt ? __ldcs(vb + i) : 0.0;
     }
+    // the block's slice of the row pointer, coalesced, once (needed after the barrier only)
+    for (int i = threadIdx.x; i <= nr; i += kSpmvBlock) rp[i] = rowptr[r0 + i];
     double xv[kNt];
 #pragma unroll
     for (int t = 0; t < kNt; ++t) xv[t] = cidx[t] >= 0 ? __ldg(x + cidx[t]) : 0.0;
@@ -148,8 +146,15 @@ static void build_row_blocks(Ctx& c, const Csr& A) {
     blk.push_back(A.nrows);
     if (!ok || A.nrows == 0) { A.nblk = 0; return; }
     A.nblk = (int)blk.size() - 1;
-    A.blk_row.alloc(blk.size());
-    PORO_CUDA(cudaMemcpyAsync(A.blk_row.p, blk.data(), blk.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+    std::vector<int> dsc((size_t)A.nblk * 4);
+    for (int b = 0; b < A.nblk; ++b) {
+        dsc[4 * b] = blk[b];
+        dsc[4 * b + 1] = blk[b + 1] - blk[b];
+        dsc[4 * b + 2] = rp[blk[b]];
+        dsc[4 * b + 3] = rp[blk[b + 1]] - rp[blk[b]];
+    }
+    A.blk_row.alloc(dsc.size());          // holds the descriptors {first row, rows, first nonzero, nonzeros}
+    PORO_CUDA(cudaMemcpyAsync(A.blk_row.p, dsc.data(), dsc.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
     PORO_CUDA(cudaStreamSynchronize(c.stream));
 }
 
@@ -202,7 +207,7 @@ static int launch_spmv(Ctx& c, const Csr& A, const double* x, double* y, const E
         grid = A.nblk;
         const double a = A.avg_row();
         const int G = a <= 1.5 ? 1 : a <= 4 ? 2 : a <= 12 ? 4 : a <= 48 ? 8 : a <= 160 ? 16 : 32;
-#define GO(GG) k_spmv_stream<GG, MODE><<<grid, kSpmvBlock, 0, c.stream>>>(A.blk_row.p, A.rowptr.p, A.col.p, A.val.p, x, y, ep, dot_partial)
+#define GO(GG) k_spmv_stream<GG, MODE><<<grid, kSpmvBlock, 0, c.stream>>>(reinterpret_cast<const int4*>(A.blk_row.p), A.rowptr.p, A.col.p, A.val.p, x, y, ep, dot_partial)
         switch (G) {
             case 1: GO(1); break;
             case 2: GO(2); break;
