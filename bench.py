@@ -202,7 +202,7 @@ def run_reference(args):
         return
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     from oracle.problems import swelling
-    N = mesh_for_gpus(args.mesh_n, max(world, args.gpus))
+    N = args.total_mesh_n or mesh_for_gpus(args.mesh_n, max(world, args.gpus))
     if N > args.cpu_max_n:
         # the numpy set-up of the port does not fit the time budget beyond this size: say so instead of timing another problem
         print(json.dumps({"impl": "reference", "unavailable": "CPU oracle port set-up at mesh N=%d exceeds the time budget "
@@ -270,6 +270,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--mesh-n", type=int, default=34, help="cells per side at 1 GPU (swelling-3d.py -N)")
+    ap.add_argument("--total-mesh-n", type=int, default=0, help="cells per side of the WHOLE mesh at this GPU count (overrides the weak-scaling "
+                    "rule; e.g. 101 = BASELINE config 5, 51.3 M DoFs)")
     ap.add_argument("--cpu-sample-n", type=int, default=0, help="(unused since round 2: the CPU arm runs the GPU arm's own mesh)")
     ap.add_argument("--cpu-max-n", type=int, default=40, help="largest mesh the CPU oracle port is set up for")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -302,7 +304,7 @@ def main():
 
     # ---- set-up (untimed): generate (or assemble) the system, build the preconditioner
     t_asm = time.perf_counter()
-    N = mesh_for_gpus(args.mesh_n, world)
+    N = args.total_mesh_n or mesh_for_gpus(args.mesh_n, world)
     gen_sys = None
     if args.assemble == "device":
         from poro_b200.generator import generate_swelling3d

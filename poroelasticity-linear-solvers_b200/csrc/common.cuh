@@ -262,6 +262,8 @@ void vec_dots(Ctx& c, int k, const double* const* xs, const double* const* ys, i
 void vec_mdot(Ctx& c, const double* V, int64_t ld, int ncol, const double* w, int64_t n, double* d_h, bool with_ww);
 // w -= V h (h device, ncol entries); d_nrm2 (device, 1 double) receives ||w_new||^2 (local)
 void vec_maxpy_norm(Ctx& c, double* w, const double* V, int64_t ld, int ncol, const double* d_h, int64_t n, double* d_nrm2);
+// w = scale * (w - V h): projection and normalisation in one pass (h device, ncol entries)
+void vec_maxpy_scale(Ctx& c, double* w, const double* V, int64_t ld, int ncol, const double* d_h, int64_t n, double scale);
 // y += V h with host coefficients (solution update)
 void vec_maxpy_host(Ctx& c, double* y, const double* V, int64_t ld, int ncol, const double* h_host, int64_t n);
 // sum over ranks in place (no-op on one rank), then copy to host and synchronise

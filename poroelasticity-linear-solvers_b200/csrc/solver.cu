@@ -186,6 +186,7 @@ void KSP::set_from_options(const std::string& pre) {
     if (ref == "refine_always") cgs2 = true;
     if (ref == "refine_never") cgs2 = false;
     monitor = c.has_opt(key("ksp_monitor"));
+    fused_gs = c.opt_i("-poro_gmres_fused_gs", 1) != 0;
     converged_reason = c.has_opt(key("ksp_converged_reason"));
     if (c.has_opt(key("ksp_initial_guess_nonzero"))) {
         std::string v = c.opt(key("ksp_initial_guess_nonzero"), "");
@@ -371,25 +372,51 @@ void KSP::solve_gmres(const double* b, double* x, bool flexible) {
             if (flexible) { double* zj = Z.p + (size_t)j * n; pc->apply(vj, zj); op_apply(zj, w); }
             else if (rpc) { pc->apply(vj, w1.p); op_apply(w1.p, w); }
             else { op_apply(vj, w1.p); pc->apply(w1.p, w); }
-            // classical Gram-Schmidt: one multi-dot pass, one multi-axpy(+norm) pass
+            // classical Gram-Schmidt.  Without refinement: ONE multi-dot pass that also returns w.w, one all-reduce, one read-back;
+            // the norm of the projected vector follows from Pythagoras (||w - V h||^2 = w.w - h.h, V orthonormal) and the
+            // update and the normalisation are ONE pass, w = (w - V h) / ||.||.  When the difference cancels (the new
+            // direction is almost in the span) or with refinement the explicit two-pass form below is used.
+            double hn = 0.0;
+            bool scaled = false;
             {
                 ProfScope ps_gs(c, 5);
-                vec_mdot(c, V.p, n, j + 1, w, n, d_h, false);
-                allreduce_sum(c, d_h, j + 1);
-                vec_maxpy_norm(c, w, V.p, n, j + 1, d_h, n, d_h + 2 * (m + 1));
-                if (cgs2) {
-                    double* d_h2 = d_h + (m + 1);
-                    vec_mdot(c, V.p, n, j + 1, w, n, d_h2, false);
-                    allreduce_sum(c, d_h2, j + 1);
-                    vec_maxpy_norm(c, w, V.p, n, j + 1, d_h2, n, d_h + 2 * (m + 1));
+                if (!cgs2 && fused_gs) {
+                    vec_mdot(c, V.p, n, j + 1, w, n, d_h, true);
+                    allreduce_sum(c, d_h, j + 2);
+                    fetch(c, d_h, j + 2, hbuf.data());
+                    double hh = 0.0;
+                    for (int i = 0; i <= j; ++i) hh += hbuf[i] * hbuf[i];
+                    const double ww = hbuf[j + 1], hn2 = ww - hh;
+                    if (hn2 > 1e-4 * ww) {
+                        hn = std::sqrt(hn2);
+                        vec_maxpy_scale(c, w, V.p, n, j + 1, d_h, n, 1.0 / hn);
+                        scaled = true;
+                    } else {
+                        vec_maxpy_norm(c, w, V.p, n, j + 1, d_h, n, d_h + 2 * (m + 1));
+                        allreduce_sum(c, d_h + 2 * (m + 1), 1);
+                        double nn2;
+                        fetch(c, d_h + 2 * (m + 1), 1, &nn2);
+                        hn = std::sqrt(nn2);
+                    }
+                    for (int i = 0; i <= j; ++i) hbuf[(m + 1) + i] = 0.0;
+                } else {
+                    vec_mdot(c, V.p, n, j + 1, w, n, d_h, false);
+                    allreduce_sum(c, d_h, j + 1);
+                    vec_maxpy_norm(c, w, V.p, n, j + 1, d_h, n, d_h + 2 * (m + 1));
+                    if (cgs2) {
+                        double* d_h2 = d_h + (m + 1);
+                        vec_mdot(c, V.p, n, j + 1, w, n, d_h2, false);
+                        allreduce_sum(c, d_h2, j + 1);
+                        vec_maxpy_norm(c, w, V.p, n, j + 1, d_h2, n, d_h + 2 * (m + 1));
+                    }
+                    allreduce_sum(c, d_h + 2 * (m + 1), 1);
+                    fetch(c, d_h, 2 * (m + 1) + 1, hbuf.data());
+                    hn = std::sqrt(hbuf[2 * (m + 1)]);
                 }
-                allreduce_sum(c, d_h + 2 * (m + 1), 1);
-                fetch(c, d_h, 2 * (m + 1) + 1, hbuf.data());
             }
             for (int i = 0; i <= j; ++i) Hm(i, j) = hbuf[i] + (cgs2 ? hbuf[(m + 1) + i] : 0.0);
-            double hn = std::sqrt(hbuf[2 * (m + 1)]);
             Hm(j + 1, j) = hn;
-            if (hn > 0.0) vec_scale(c, w, 1.0 / hn, n);
+            if (hn > 0.0 && !scaled) vec_scale(c, w, 1.0 / hn, n);
             for (int i = 0; i < j; ++i) {
                 double t = cs[i] * Hm(i, j) + sn[i] * Hm(i + 1, j);
                 Hm(i + 1, j) = -sn[i] * Hm(i, j) + cs[i] * Hm(i + 1, j);

@@ -101,6 +101,7 @@ struct KSP {
     int max_it = 10000, restart = 30;
     bool right = false, unprec_norm = false, natural_norm = false, cgs2 = false;
     bool monitor = false;
+    bool fused_gs = true;               // one-pass projection + normalisation with the Pythagorean norm (plain CGS only)
     bool converged_reason = false;      // -<prefix>ksp_converged_reason
     bool guess_nonzero = false;         // KSPSetInitialGuessNonzero / -<prefix>ksp_initial_guess_nonzero (warm start over time steps)
     // per-field infinity-norm residual monitor / convergence test: the `converged` callback of lib/Solver.py:8-51

@@ -265,6 +265,49 @@ __global__ void __launch_bounds__(kBlock) k_maxpy_norm(double* __restrict__ w, c
     }
 }
 
+// w = scale * (w - V h): the Gram-Schmidt update and the normalisation of the new basis vector in one pass
+__global__ void __launch_bounds__(kBlock) k_maxpy_scale(double* __restrict__ w, const double* __restrict__ V, int64_t ld,
+                                                        int ncol, const double* __restrict__ h, int64_t n, double scale) {
+    extern __shared__ double hs[];
+    for (int j = threadIdx.x; j < ncol; j += kBlock) hs[j] = h[j];
+    __syncthreads();
+    const int64_t tile = (int64_t)kBlock * kRpt;
+    for (int64_t base = (int64_t)blockIdx.x * tile; base < n; base += (int64_t)gridDim.x * tile) {
+        double wv[kRpt];
+        int64_t row[kRpt];
+#pragma unroll
+        for (int r = 0; r < kRpt; ++r) {
+            row[r] = base + (int64_t)r * kBlock + threadIdx.x;
+            wv[r] = row[r] < n ? w[row[r]] : 0.0;
+        }
+        for (int c0 = 0; c0 < ncol; c0 += kCchunk) {
+            double v[kCchunk][kRpt];
+#pragma unroll
+            for (int cc = 0; cc < kCchunk; ++cc) {
+                const double* col = V + (int64_t)(c0 + cc) * ld;
+#pragma unroll
+                for (int r = 0; r < kRpt; ++r) v[cc][r] = (c0 + cc < ncol && row[r] < n) ? col[row[r]] : 0.0;
+            }
+#pragma unroll
+            for (int cc = 0; cc < kCchunk; ++cc) {
+                double hc = c0 + cc < ncol ? hs[c0 + cc] : 0.0;
+#pragma unroll
+                for (int r = 0; r < kRpt; ++r) wv[r] = fma(-hc, v[cc][r], wv[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kRpt; ++r)
+            if (row[r] < n) w[row[r]] = wv[r] * scale;
+    }
+}
+
+void vec_maxpy_scale(Ctx& c, double* w, const double* V, int64_t ld, int ncol, const double* d_h, int64_t n, double scale) {
+    int grid = stream_grid(c, n, kBlock, kRpt, 2);
+    size_t smem = (size_t)(ncol > 0 ? ncol : 1) * sizeof(double);
+    k_maxpy_scale<<<grid, kBlock, smem, c.stream>>>(w, V, ld, ncol, d_h, n, scale);
+    PORO_LAUNCH_CHECK(c);
+}
+
 void vec_maxpy_norm(Ctx& c, double* w, const double* V, int64_t ld, int ncol, const double* d_h, int64_t n, double* d_nrm2) {
     int grid = stream_grid(c, n, kBlock, kRpt, 2);
     size_t smem = (size_t)(ncol > 0 ? ncol : 1) * sizeof(double);
