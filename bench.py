@@ -42,6 +42,7 @@ os.environ.setdefault("PORO_LOG_STDERR", "1")      # stdout carries only the JSO
 BENCH_OPTIONS = """
 -global_ksp_type gmres
 -global_ksp_pc_side right
+-global_ksp_gmres_verify_true_residual 1
 -s_ksp_type preonly
 -s_pc_type hypre
 -s_pc_amg_theta 0.04
@@ -416,7 +417,7 @@ def main():
         import torch.distributed as dist
         dist.all_reduce(sums)
     true_res = float(torch.sqrt(sums[0] / sums[1]))
-    ok = reason > 0 and true_res <= 10 * RTOL
+    ok = reason > 0 and true_res <= 1.01 * RTOL          # the TRUE residual, not the recurrence's estimate
 
     if rank != 0:
         if world > 1:

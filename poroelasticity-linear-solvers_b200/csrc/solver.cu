@@ -187,6 +187,7 @@ void KSP::set_from_options(const std::string& pre) {
     if (ref == "refine_never") cgs2 = false;
     monitor = c.has_opt(key("ksp_monitor"));
     fused_gs = c.opt_i("-poro_gmres_fused_gs", 1) != 0;
+    verify_true = c.has_opt(key("ksp_gmres_verify_true_residual")) && c.opt(key("ksp_gmres_verify_true_residual"), "1") != "0";
     converged_reason = c.has_opt(key("ksp_converged_reason"));
     if (c.has_opt(key("ksp_initial_guess_nonzero"))) {
         std::string v = c.opt(key("ksp_initial_guess_nonzero"), "");
@@ -445,6 +446,17 @@ void KSP::solve_gmres(const double* b, double* x, bool flexible) {
             if (hn == 0.0 && reason == 0) reason = 2;
         }
         add_correction(x, j);
+        if (verify_true && rpc && !flexible && reason > 0 && its < max_it && j > 0) {
+            // The Arnoldi recurrence said "converged"; classical Gram-Schmidt loses orthogonality over long cycles, so check the
+            // TRUE residual b - A x (for right preconditioning it is what the recurrence estimates) and, if it is not there
+            // yet, restart from x and keep iterating.  PETSc leaves this to the user (-ksp_gmres_cgs_refinement_type).
+            A->apply(x, w1.p, SPMV_SUB, b);
+            const double tr = norm2_host(c, w1.p, n);
+            if (tr > ttol) {
+                if (monitor && c.rank == 0) printf("  %s true residual %.6e above tolerance %.6e after %d iterations: restarting\n", prefix.c_str(), tr, ttol, its);
+                reason = 0;
+            } else history.back() = tr;
+        }
         if (reason == 0 && its >= max_it) reason = -3;
     }
     rnorm = history.empty() ? 0.0 : history.back();
