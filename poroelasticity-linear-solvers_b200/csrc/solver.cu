@@ -310,7 +310,10 @@ void KSP::solve_gmres(const double* b, double* x, bool flexible) {
     if (flexible && (int64_t)Z.n < (int64_t)m * n) Z.alloc((size_t)m * n);
     if ((int64_t)w1.n < n) { w1.alloc(n); w2.alloc(n); }
     DBuf<double> xtmp;
-    if (use_fields) xtmp.alloc(n);
+    if (use_fields || verify_true) xtmp.alloc(n);
+    bool refine = cgs2;          // second Gram-Schmidt pass; switched on for the rest of a solve when a verification fails
+    double calib = 1.0;          // measured ratio (true residual) / (recurrence estimate), applied to the convergence test
+    bool x_final = false;        // x already holds the verified solution of the current cycle
     std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), hbuf(2 * (m + 1) + 2);
     auto Hm = [&](int i, int j) -> double& { return H[(size_t)i * m + j]; };
     double* d_h = c.d_scal + Ctx::kScal + 4096 + 16;   // [h (m+1) | h2 (m+1) | nrm2]; small-slot region
@@ -381,7 +384,7 @@ void KSP::solve_gmres(const double* b, double* x, bool flexible) {
             bool scaled = false;
             {
                 ProfScope ps_gs(c, 5);
-                if (!cgs2 && fused_gs) {
+                if (!refine && fused_gs) {
                     vec_mdot(c, V.p, n, j + 1, w, n, d_h, true);
                     allreduce_sum(c, d_h, j + 2);
                     fetch(c, d_h, j + 2, hbuf.data());
@@ -404,7 +407,7 @@ void KSP::solve_gmres(const double* b, double* x, bool flexible) {
                     vec_mdot(c, V.p, n, j + 1, w, n, d_h, false);
                     allreduce_sum(c, d_h, j + 1);
                     vec_maxpy_norm(c, w, V.p, n, j + 1, d_h, n, d_h + 2 * (m + 1));
-                    if (cgs2) {
+                    if (refine) {
                         double* d_h2 = d_h + (m + 1);
                         vec_mdot(c, V.p, n, j + 1, w, n, d_h2, false);
                         allreduce_sum(c, d_h2, j + 1);
@@ -415,7 +418,7 @@ void KSP::solve_gmres(const double* b, double* x, bool flexible) {
                     hn = std::sqrt(hbuf[2 * (m + 1)]);
                 }
             }
-            for (int i = 0; i <= j; ++i) Hm(i, j) = hbuf[i] + (cgs2 ? hbuf[(m + 1) + i] : 0.0);
+            for (int i = 0; i <= j; ++i) Hm(i, j) = hbuf[i] + (refine ? hbuf[(m + 1) + i] : 0.0);
             Hm(j + 1, j) = hn;
             if (hn > 0.0 && !scaled) vec_scale(c, w, 1.0 / hn, n);
             for (int i = 0; i < j; ++i) {
@@ -436,7 +439,28 @@ void KSP::solve_gmres(const double* b, double* x, bool flexible) {
             double res = std::fabs(g[j]);
             history.push_back(res);
             if (monitor && c.rank == 0) printf("  %s KSP residual norm[%d] %.12e\n", prefix.c_str(), its, res);
-            reason = converged(res, its, rnorm0, ttol);
+            reason = converged(res * calib, its, rnorm0, ttol);
+            if (reason > 0 && verify_true && rpc && !flexible) {
+                // The recurrence says "converged".  Classical Gram-Schmidt loses orthogonality over long cycles and the
+                // estimate then runs ahead of the true residual: form the candidate solution, check b - A x, and if it is not
+                // there yet KEEP the Krylov space, calibrate the estimate, switch the second Gram-Schmidt pass on and go on.
+                vec_copy(c, xtmp.p, x, n);
+                add_correction(xtmp.p, j);
+                A->apply(xtmp.p, w1.p, SPMV_SUB, b);
+                const double tr = norm2_host(c, w1.p, n);
+                if (tr <= ttol) {
+                    vec_copy(c, x, xtmp.p, n);
+                    history.back() = tr;
+                    x_final = true;
+                } else {
+                    if (monitor && c.rank == 0)
+                        printf("  %s true residual %.6e (estimate %.6e) above %.6e at iteration %d: continuing with refinement\n",
+                               prefix.c_str(), tr, res, ttol, its);
+                    calib = std::max(calib, 1.1 * tr / std::max(res, 1e-300));
+                    refine = true;
+                    reason = 0;
+                }
+            }
             if (use_fields) {
                 vec_copy(c, xtmp.p, x, n);
                 add_correction(xtmp.p, j);
@@ -445,18 +469,7 @@ void KSP::solve_gmres(const double* b, double* x, bool flexible) {
             }
             if (hn == 0.0 && reason == 0) reason = 2;
         }
-        add_correction(x, j);
-        if (verify_true && rpc && !flexible && reason > 0 && its < max_it && j > 0) {
-            // The Arnoldi recurrence said "converged"; classical Gram-Schmidt loses orthogonality over long cycles, so check the
-            // TRUE residual b - A x (for right preconditioning it is what the recurrence estimates) and, if it is not there
-            // yet, restart from x and keep iterating.  PETSc leaves this to the user (-ksp_gmres_cgs_refinement_type).
-            A->apply(x, w1.p, SPMV_SUB, b);
-            const double tr = norm2_host(c, w1.p, n);
-            if (tr > ttol) {
-                if (monitor && c.rank == 0) printf("  %s true residual %.6e above tolerance %.6e after %d iterations: restarting\n", prefix.c_str(), tr, ttol, its);
-                reason = 0;
-            } else history.back() = tr;
-        }
+        if (!x_final) add_correction(x, j);
         if (reason == 0 && its >= max_it) reason = -3;
     }
     rnorm = history.empty() ? 0.0 : history.back();

@@ -64,7 +64,7 @@ def test_gpu_gmres_reproduces_golden(gpu_ctx, path):
     loose = "undrained" in s.pc_type
     assert out["its"] == int(g["gmres_its"])
     np.testing.assert_allclose(out["history"], g["gmres_history"], rtol=5e-3 if loose else 1e-6, atol=1e-14)
-    assert rel(out["x"], g["gmres_x"]) <= (1e-6 if loose else 1e-8)
+    assert rel(out["x"], g["gmres_x"]) <= 1e-8          # `undrained` too: the dense exact blocks are refined once (PCDense)
 
 
 @pytest.mark.gpu
