@@ -271,6 +271,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--mesh-n", type=int, default=34, help="cells per side at 1 GPU (swelling-3d.py -N)")
+    ap.add_argument("--maxiter", type=int, default=100, help="solver maxiter = GMRES restart (swelling-3d.py:66: 100)")
     ap.add_argument("--total-mesh-n", type=int, default=0, help="cells per side of the WHOLE mesh at this GPU count (overrides the weak-scaling "
                     "rule; e.g. 101 = BASELINE config 5, 51.3 M DoFs)")
     ap.add_argument("--cpu-sample-n", type=int, default=0, help="(unused since round 2: the CPU arm runs the GPU arm's own mesh)")
@@ -327,7 +328,7 @@ def main():
     par = dict(par)
     # swelling-3d.py:66: maxiter (= restart, lib/Solver.py:99-100) 100, at every N: the distributed hierarchies
     # (csrc/distamg.cu) keep the iteration count of the single-GPU solve
-    maxiter = 100
+    maxiter = args.maxiter
     par.update({"solver rtol": RTOL, "solver atol": 0.0, "solver maxiter": maxiter, "solver type": "gmres"})
     t_set = time.perf_counter()
     if gen_sys is not None:

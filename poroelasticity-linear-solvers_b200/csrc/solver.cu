@@ -186,7 +186,7 @@ void KSP::set_from_options(const std::string& pre) {
     if (ref == "refine_always") cgs2 = true;
     if (ref == "refine_never") cgs2 = false;
     monitor = c.has_opt(key("ksp_monitor"));
-    fused_gs = c.opt_i("-poro_gmres_fused_gs", 1) != 0;
+    fused_gs = c.opt_i("-poro_gmres_fused_gs", 0) != 0;
     verify_true = c.has_opt(key("ksp_gmres_verify_true_residual")) && c.opt(key("ksp_gmres_verify_true_residual"), "1") != "0";
     converged_reason = c.has_opt(key("ksp_converged_reason"));
     if (c.has_opt(key("ksp_initial_guess_nonzero"))) {
@@ -376,10 +376,11 @@ void KSP::solve_gmres(const double* b, double* x, bool flexible) {
             if (flexible) { double* zj = Z.p + (size_t)j * n; pc->apply(vj, zj); op_apply(zj, w); }
             else if (rpc) { pc->apply(vj, w1.p); op_apply(w1.p, w); }
             else { op_apply(vj, w1.p); pc->apply(w1.p, w); }
-            // classical Gram-Schmidt.  Without refinement: ONE multi-dot pass that also returns w.w, one all-reduce, one read-back;
-            // the norm of the projected vector follows from Pythagoras (||w - V h||^2 = w.w - h.h, V orthonormal) and the
-            // update and the normalisation are ONE pass, w = (w - V h) / ||.||.  When the difference cancels (the new
-            // direction is almost in the span) or with refinement the explicit two-pass form below is used.
+            // classical Gram-Schmidt: one multi-dot pass, one multi-axpy(+norm) pass, one scaling pass.
+            // (-poro_gmres_fused_gs 1 takes the norm from Pythagoras, ||w - V h||^2 = w.w - h.h, and fuses update and scaling
+            // into one pass.  MEASURED TO BE UNSAFE with unrefined CGS: as orthogonality of V degrades the identity is off by
+            // O(loss) * w.w, which is of the size of the norm itself late in a solve; the Arnoldi relation breaks and the
+            // recurrence residual stalls while the true one keeps falling (100 instead of 36 iterations).  Off by default.)
             double hn = 0.0;
             bool scaled = false;
             {

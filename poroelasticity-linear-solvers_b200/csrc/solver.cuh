@@ -102,7 +102,7 @@ struct KSP {
     bool right = false, unprec_norm = false, natural_norm = false, cgs2 = false;
     bool monitor = false;
     bool verify_true = false;           // -<prefix>ksp_gmres_verify_true_residual: confirm convergence with b - A x, restart if needed
-    bool fused_gs = true;               // one-pass projection + normalisation with the Pythagorean norm (plain CGS only)
+    bool fused_gs = false;              // one-pass projection + normalisation with the Pythagorean norm: unsafe, see solve_gmres
     bool converged_reason = false;      // -<prefix>ksp_converged_reason
     bool guess_nonzero = false;         // KSPSetInitialGuessNonzero / -<prefix>ksp_initial_guess_nonzero (warm start over time steps)
     // per-field infinity-norm residual monitor / convergence test: the `converged` callback of lib/Solver.py:8-51
