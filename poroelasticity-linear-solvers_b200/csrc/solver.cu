@@ -309,8 +309,7 @@ void KSP::solve_gmres(const double* b, double* x, bool flexible) {
     if (v_cols < m + 1 || (int64_t)V.n < (int64_t)(m + 1) * n) { V.alloc((size_t)(m + 1) * n); v_cols = m + 1; }
     if (flexible && (int64_t)Z.n < (int64_t)m * n) Z.alloc((size_t)m * n);
     if ((int64_t)w1.n < n) { w1.alloc(n); w2.alloc(n); }
-    DBuf<double> xtmp;
-    if (use_fields || verify_true) xtmp.alloc(n);
+    if ((use_fields || verify_true) && (int64_t)xtmp.n < n) xtmp.alloc(n);      // persistent: no allocation inside a solve
     bool refine = cgs2;          // second Gram-Schmidt pass; switched on for the rest of a solve when a verification fails
     double calib = 1.0;          // measured ratio (true residual) / (recurrence estimate), applied to the convergence test
     bool x_final = false;        // x already holds the verified solution of the current cycle

@@ -117,7 +117,7 @@ struct KSP {
     std::vector<double> history;
     int64_t total_its = 0, calls = 0;
     // work
-    DBuf<double> V, Z, w1, w2, w3;
+    DBuf<double> V, Z, w1, w2, w3, xtmp;
     int v_cols = 0;
     // optional live profile of the operator product (CUDA events on the launching stream)
     bool profile_op = false;
