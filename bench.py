@@ -203,12 +203,15 @@ def run_reference(args):
         return
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     from oracle.problems import swelling
-    N = args.total_mesh_n or mesh_for_gpus(args.mesh_n, max(world, args.gpus))
+    N_arm = args.total_mesh_n or mesh_for_gpus(args.mesh_n, max(world, args.gpus))
+    N = N_arm
+    same = True
     if N > args.cpu_max_n:
-        # the numpy set-up of the port does not fit the time budget beyond this size: say so instead of timing another problem
-        print(json.dumps({"impl": "reference", "unavailable": "CPU oracle port set-up at mesh N=%d exceeds the time budget "
-                          "(limit N=%d); same-config reference exists at 1 GPU only" % (N, args.cpu_max_n)}))
-        return
+        # the numpy set-up of the port does not fit the time budget on the weak-scaled mesh: the bounded sample is the
+        # per-GPU share of the workload (the 1-GPU mesh).  DoF/s on the smaller mesh is an UPPER bound for the port's DoF/s on
+        # the larger one (the iteration count grows with the mesh), i.e. the comparison errs in the CPU's favour.
+        N = min(args.mesh_n, args.cpu_max_n)
+        same = False
     sys_, par = swelling(3, N, "diagonal")
     runs = oracle_solver(sys_, par, 100)
     label = [k for k in runs if k.startswith("C + OpenMP")]
@@ -231,9 +234,12 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "steps_timed": steps_timed,
-            "config": {"workload": workload_text(N, sys_.n, sys_.A.nnz, 100, "maxiter", 1), "same_config_as_gpu_arm": True,
+            "config": {"workload": workload_text(N, sys_.n, sys_.A.nnz, 100, "maxiter", 1), "same_config_as_gpu_arm": same,
+                       "gpu_arm_mesh_n": N_arm,
                        "note": "CPU oracle port (numpy set-up + C/OpenMP solve loop), NOT PETSc/hypre; each step = one full "
-                               "solve, %d of the %d requested steps executed (bounded sample)" % (steps_timed, args.steps)},
+                               "solve, %d of the %d requested steps executed (bounded sample)%s" % (
+                                   steps_timed, args.steps, "" if same else "; sample = the 1-GPU mesh (per-GPU share of the "
+                                   "weak-scaled workload): the port's set-up of the N=%d mesh does not fit the time budget" % N_arm)},
             "time_to_1e-8_s": dt, "its_per_solve": its / steps_timed, "true_rel_residual": res,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "port",
                              "sample": "mesh N=%d (%d DoFs), %d full solves, %s; NOT PETSc/hypre" % (N, sys_.n, steps_timed, label)},
