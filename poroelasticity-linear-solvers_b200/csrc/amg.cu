@@ -361,6 +361,62 @@ static double power_lmax_dist(Ctx& c, const Csr& A, DistPlan& plan, const double
     return lam;
 }
 
+// gathers a distributed level operator (local rows x [owned | ghost]) and its near-nullspace rows on EVERY rank
+static void gather_level(Ctx& c, const Csr& A, const DistPlan& plan, const double* B, int k, Csr& Ag, DBuf<double>& Bg) {
+    const int R = c.nranks;
+    const int64_t ng = plan.offsets.back();
+    Csr Al;
+    csr_copy(c, A, Al);
+    dist_globalize(c, Al, plan, ng);
+    std::vector<int64_t> mine = {(int64_t)Al.nrows, Al.nnz}, all;
+    dist_allgather_i64(c, mine.data(), 2, all);
+    int64_t maxr = 1, maxz = 1, nnz_tot = 0;
+    for (int r = 0; r < R; ++r) { maxr = std::max(maxr, all[2 * r]); maxz = std::max(maxz, all[2 * r + 1]); nnz_tot += all[2 * r + 1]; }
+    PORO_REQUIRE(nnz_tot < 2147483647LL, "gathered level too large");
+    DBuf<int> slen((size_t)maxr), glen((size_t)R * maxr), scol((size_t)maxz), gcol((size_t)R * maxz);
+    DBuf<double> sval((size_t)maxz), gval((size_t)R * maxz), sB((size_t)maxr * k), gB((size_t)R * maxr * k);
+    slen.zero(c.stream); scol.zero(c.stream); sval.zero(c.stream); sB.zero(c.stream);
+    {
+        const int* rp = Al.rowptr.p; int* L = slen.p;
+        pfor(c, Al.nrows, [=] __device__(int64_t i) { L[i] = rp[i + 1] - rp[i]; });
+    }
+    if (Al.nnz) {
+        PORO_CUDA(cudaMemcpyAsync(scol.p, Al.col.p, (size_t)Al.nnz * sizeof(int), cudaMemcpyDeviceToDevice, c.stream));
+        PORO_CUDA(cudaMemcpyAsync(sval.p, Al.val.p, (size_t)Al.nnz * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+    }
+    if (Al.nrows) PORO_CUDA(cudaMemcpyAsync(sB.p, B, (size_t)Al.nrows * k * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+    dist_allgather_bytes(c, slen.p, (size_t)maxr * sizeof(int), glen.p);
+    dist_allgather_bytes(c, scol.p, (size_t)maxz * sizeof(int), gcol.p);
+    dist_allgather_bytes(c, sval.p, (size_t)maxz * sizeof(double), gval.p);
+    dist_allgather_bytes(c, sB.p, (size_t)maxr * k * sizeof(double), gB.p);
+    Ag.nrows = (int)ng; Ag.ncols = (int)ng; Ag.nnz = nnz_tot;
+    Ag.rowptr.alloc((size_t)ng + 1); Ag.col.alloc((size_t)nnz_tot); Ag.val.alloc((size_t)nnz_tot);
+    Bg.alloc((size_t)ng * k);
+    DBuf<int64_t> len64((size_t)ng + 1), ptr64((size_t)ng + 1);
+    len64.zero(c.stream);
+    int64_t zoff = 0;
+    for (int r = 0; r < R; ++r) {
+        const int64_t rows = all[2 * r], nz = all[2 * r + 1], ro = plan.offsets[r];
+        {
+            const int* src = glen.p + (size_t)r * maxr; int64_t* dst = len64.p + ro;
+            pfor(c, rows, [=] __device__(int64_t i) { dst[i] = src[i]; });
+        }
+        if (nz) {
+            PORO_CUDA(cudaMemcpyAsync(Ag.col.p + zoff, gcol.p + (size_t)r * maxz, (size_t)nz * sizeof(int), cudaMemcpyDeviceToDevice, c.stream));
+            PORO_CUDA(cudaMemcpyAsync(Ag.val.p + zoff, gval.p + (size_t)r * maxz, (size_t)nz * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+        }
+        if (rows) PORO_CUDA(cudaMemcpyAsync(Bg.p + (size_t)ro * k, gB.p + (size_t)r * maxr * k, (size_t)rows * k * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+        zoff += nz;
+    }
+    scan_i64(c, len64.p, ptr64.p, ng + 1);
+    {
+        const int64_t* s64 = ptr64.p; int* rp = Ag.rowptr.p;
+        pfor(c, ng + 1, [=] __device__(int64_t i) { rp[i] = (int)s64[i]; });
+    }
+    PORO_CUDA(cudaStreamSynchronize(c.stream));
+    csr_choose_lanes(Ag);
+}
+
 // ---- set-up ---------------------------------------------------------------------------------
 void Amg::setup(Ctx& c, const Csr& A, int bs, const double* B_dev, int k, const AmgParams& p, DistPlan* plan0) {
     dist = plan0 != nullptr && c.nranks > 1;
@@ -401,6 +457,27 @@ void Amg::setup(Ctx& c, const Csr& A, int bs, const double* B_dev, int k, const 
         n = Acur->nrows;
         const int n_gh = dist ? Lp->plan->n_ghost : 0;
         const int64_t n_glob = dist ? Lp->plan->offsets.back() : n;
+        if (dist && levels.size() >= 2 && !par.smoother_only && n_glob > par.coarse_size &&
+            n_glob <= c.opt_i("-poro_amg_replicate_below", 60000)) {
+            // latency-bound level: gather it once, build and cycle the rest of the hierarchy redundantly on every rank
+            Tick t(c, "gathered tail hierarchy");
+            DBuf<double> Bg;
+            gather_level(c, *Acur, *Lp->plan, B.p, k, tail_A, Bg);
+            tail_A.block_hint = bs;
+            tail = std::make_unique<Amg>();
+            AmgParams tp = par;
+            tp.max_levels = std::max(1, par.max_levels - (int)levels.size() + 1);
+            tail->setup(c, tail_A, bs, Bg.p, k, tp, nullptr);
+            tail_b.alloc((size_t)n_glob);
+            tail_x.alloc((size_t)n_glob);
+            Lp->replicated = true;
+            Lp->x.alloc((size_t)n + n_gh);
+            Lp->b.alloc(n);
+            if (verbose && c.rank == 0)
+                fprintf(stderr, "    [amg] level %d: %lld global rows gathered on every rank, %d redundant levels below\n", (int)levels.size() - 1,
+                        (long long)n_glob, (int)tail->levels.size());
+            break;
+        }
         make_dinv(c, *Acur, Lp->dinv);
         {
             Tick t(c, "power iteration");
@@ -495,6 +572,11 @@ void Amg::setup(Ctx& c, const Csr& A, int bs, const double* B_dev, int k, const 
         B = std::move(Bc);
         bs = k;
     }
+    if (tail) {                                    // the redundant tail owns the coarsest level
+        coarse_direct = false;
+        PORO_CUDA(cudaStreamSynchronize(c.stream));
+        return;
+    }
     // coarsest level: dense inverse when small enough (gathered on every rank in a distributed hierarchy)
     const int lc = (int)levels.size() - 1;
     const Csr& Ac = op(lc);
@@ -540,6 +622,7 @@ const double* Amg::ext(int l, const double* v) {
     Ctx& c = *ctx;
     AmgLevel& L = *levels[l];
     const int n = L.plan->n_owned;
+    if (L.replicated && v == L.x.p) return v;      // ghosts were taken from the replicated vector (cycle)
     double* dst;
     if (v == L.x.p || v == L.r.p || v == L.d0.p || v == L.d1.p) dst = const_cast<double*>(v);   // stored extended: halo lands in place
     else { vec_copy(c, L.ext.p, v, n); dst = L.ext.p; }
@@ -596,6 +679,15 @@ void Amg::cycle(int l, const double* b, double* x) {
     ProfScope ps(c, prof_base >= 0 && l < 8 ? prof_base + l : -1);
     const Csr& A = op(l);
     const int last = (int)levels.size() - 1;
+    if (levels[l]->replicated) {
+        // one all-gather of the right-hand side, the redundant sub-cycle, then this rank's slice and its ghosts
+        DistPlan& pl = *levels[l]->plan;
+        dist_allgather_slices(c, b, pl.offsets, tail_b.p);
+        tail->cycle(0, tail_b.p, tail_x.p);
+        const double* full = tail_x.p; const int* gid = pl.ghost_gid.p; const int no = pl.n_owned; const int64_t off = pl.offset;
+        pfor(c, (int64_t)no + pl.n_ghost, [=] __device__(int64_t i) { x[i] = i < no ? full[off + i] : full[gid[i - no]]; });
+        return;
+    }
     if (l == last) {
         if (coarse_direct && !dist) dense_gemv(c, coarse_inv.p, A.nrows, b, x);
         else if (coarse_direct) {

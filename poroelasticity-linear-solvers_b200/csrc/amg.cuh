@@ -27,6 +27,7 @@ struct AmgLevel {
     // distributed hierarchy: halo plan of this level's operator (level 0 borrows the plan of the block operator)
     DistPlan* plan = nullptr;
     std::unique_ptr<DistPlan> owned_plan;
+    bool replicated = false;        // this level and everything below is gathered on every rank and cycled redundantly (Amg::tail)
     DBuf<double> ext;               // staging for vectors that are not stored extended (the caller's x on level 0)
 };
 
@@ -41,6 +42,12 @@ struct Amg {
     // aggregates stay inside a rank, prolongator smoothing and the Galerkin product use the distributed operator
     // (distamg.cu); the coarsest operator is gathered on every rank.  Without a plan the hierarchy is rank-local.
     bool dist = false;
+    // small distributed levels are latency-bound (6 halo exchanges per level visit): below `-poro_amg_replicate_below` global
+    // rows a level is gathered ONCE at set-up, the rest of the hierarchy is built and cycled redundantly on every rank, and a
+    // cycle pays one all-gather of the level's right-hand side instead (oracle/distamg.py: replicate_below)
+    std::unique_ptr<Amg> tail;
+    Csr tail_A;
+    DBuf<double> tail_b, tail_x;
     int64_t coarse_n_global = 0;
     DBuf<double> coarse_full;       // gathered right-hand side of the coarsest level
     int prof_base = -1;             // phase-profile slot of level 0 (-1: not profiled)

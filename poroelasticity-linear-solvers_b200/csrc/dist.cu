@@ -133,9 +133,10 @@ struct P2PState {
     static constexpr size_t kFlagBytes = 1 << 16;   // head of the arena: 16 Ki sequence flags
     int flags_used = 16;                            // flags 0..15: small all-reduce, indexed by source rank
     // small all-reduce over peer stores: one region per source rank (2 parities x kArMax doubles) right after the flags
-    static constexpr int kArMax = 8192;
+    static constexpr int kArMax = 65536;            // doubles per source rank and parity (all-reduce: <= 8192 used; all-gather: a slice)
     static constexpr size_t kArRegion = (size_t)2 * kArMax * sizeof(double);
     uint32_t* ar_state = nullptr;                   // device: [seq]
+    unsigned* ar_ticket = nullptr;                  // device: two CTA tickets of the multi-CTA all-gather
 };
 
 struct P2PArArgs {
@@ -195,6 +196,8 @@ static void p2p_init(Ctx& c) {
     if (c.nranks <= 8 && c.opt_i("-poro_p2p_allreduce", 1)) {
         PORO_CUDA(cudaMalloc(&st->ar_state, sizeof(uint32_t)));
         PORO_CUDA(cudaMemset(st->ar_state, 0, sizeof(uint32_t)));
+        PORO_CUDA(cudaMalloc(&st->ar_ticket, 2 * sizeof(unsigned)));
+        PORO_CUDA(cudaMemset(st->ar_ticket, 0, 2 * sizeof(unsigned)));
     }
     c.p2p = st.release();
     c.p2p_fused = c.opt_i("-poro_p2p_fused", 1) != 0;
@@ -394,7 +397,7 @@ __global__ void __launch_bounds__(256) k_p2p_allreduce(P2PArArgs a, double* __re
 }
 
 static bool p2p_allreduce(Ctx& c, double* d_vals, int k) {
-    if (!c.p2p || !c.p2p->ar_state || k > P2PState::kArMax) return false;
+    if (!c.p2p || !c.p2p->ar_state || k > 8192) return false;
     P2PState& st = *c.p2p;
     P2PArArgs a{};
     a.nranks = c.nranks;
@@ -409,6 +412,89 @@ static bool p2p_allreduce(Ctx& c, double* d_vals, int k) {
     k_p2p_allreduce<<<1, 256, 0, c.stream>>>(a, d_vals, k, st.ar_state);
     PORO_LAUNCH_CHECK(c);
     return true;
+}
+
+// all-gather of one slice per rank (slice r = full[off[r] .. off[r+1])) by peer stores, same regions / flags / sequence as the
+// small all-reduce: the gathered right-hand side of a replicated coarse sub-hierarchy (amg.cu) in one launch
+struct P2PGatherOffs { int off[9]; };
+__global__ void __launch_bounds__(256) k_p2p_allgather(P2PArArgs a, P2PGatherOffs o, const double* __restrict__ mine,
+                                                       double* __restrict__ full, uint32_t* __restrict__ state,
+                                                       unsigned* __restrict__ ticket) {
+    const uint32_t seq = *state + 1u;
+    const size_t par_off = (size_t)(seq & 1u) * P2PState::kArMax;
+    const int n_mine = o.off[a.me + 1] - o.off[a.me];
+    const int stride = gridDim.x * 256, t0 = blockIdx.x * 256 + threadIdx.x;
+    for (int r = 0; r < a.nranks; ++r) {
+        if (r == a.me) continue;
+        double* dst = a.peer_region[r] + par_off;
+        for (int i = t0; i < n_mine; i += stride) dst[i] = mine[i];
+    }
+    for (int i = t0; i < n_mine; i += stride) full[o.off[a.me] + i] = mine[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(&ticket[0], 1u);
+        if (t == gridDim.x - 1) {
+            __threadfence_system();
+            for (int r = 0; r < a.nranks; ++r)
+                if (r != a.me) st_release_sys(a.peer_flag[r], seq);
+        }
+    }
+    if (threadIdx.x < a.nranks && threadIdx.x != a.me)
+        while ((int32_t)(ld_acquire_sys(a.my_flag[threadIdx.x]) - seq) < 0) { }
+    __syncthreads();
+    for (int r = 0; r < a.nranks; ++r) {
+        if (r == a.me) continue;
+        const double* src = a.my_region[r] + par_off;
+        const int n_r = o.off[r + 1] - o.off[r];
+        for (int i = t0; i < n_r; i += stride) full[o.off[r] + i] = __ldcv(src + i);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(&ticket[1], 1u);
+        if (t == gridDim.x - 1) { ticket[0] = 0u; ticket[1] = 0u; *state = seq; }
+    }
+}
+
+static void p2p_ar_args(Ctx& c, P2PArArgs& a) {
+    P2PState& st = *c.p2p;
+    a.nranks = c.nranks;
+    a.me = c.rank;
+    for (int r = 0; r < c.nranks; ++r) {
+        a.my_region[r] = (const double*)(st.arena + P2PState::kFlagBytes + (size_t)r * P2PState::kArRegion);
+        a.my_flag[r] = (const uint32_t*)st.arena + r;
+        a.peer_region[r] = r == c.rank ? nullptr : (double*)(st.peer[r] + P2PState::kFlagBytes + (size_t)c.rank * P2PState::kArRegion);
+        a.peer_flag[r] = r == c.rank ? nullptr : (uint32_t*)st.peer[r] + c.rank;
+    }
+}
+
+// full[off[r] .. off[r+1]) = slice of rank r, on every rank; offsets are element offsets (nranks + 1 entries, host)
+void dist_allgather_slices(Ctx& c, const double* mine, const std::vector<int64_t>& offs, double* full) {
+    const int R = c.nranks, me = c.rank;
+    const int64_t n_full = offs[R];
+    int64_t max_slice = 0;
+    for (int r = 0; r < R; ++r) max_slice = std::max(max_slice, offs[r + 1] - offs[r]);
+    if (R <= 1) { vec_copy(c, full, mine, n_full); return; }
+    if (c.p2p && c.p2p->ar_state && max_slice <= P2PState::kArMax && n_full < 2147483647LL) {
+        P2PArArgs a{};
+        p2p_ar_args(c, a);
+        P2PGatherOffs o{};
+        for (int r = 0; r <= R; ++r) o.off[r] = (int)offs[r];
+        const int g = (int)std::max<int64_t>(1, std::min<int64_t>((max_slice + 255) / 256, 32));
+        k_p2p_allgather<<<g, 256, 0, c.stream>>>(a, o, mine, full, c.p2p->ar_state, c.p2p->ar_ticket);
+        PORO_LAUNCH_CHECK(c);
+        return;
+    }
+    // fallback: sum of zero-padded vectors
+    PORO_CUDA(cudaMemsetAsync(full, 0, (size_t)n_full * sizeof(double), c.stream));
+    vec_copy(c, full + offs[me], mine, offs[me + 1] - offs[me]);
+    NCCL_OK(c.nccl, c.nccl->AllReduce(full, full, (size_t)n_full, NCCL_FLOAT64, NCCL_SUM, (ncclComm_p)c.comm, c.stream));
+}
+
+// equal-sized raw all-gather (set-up: gathering a coarse level operator on every rank)
+void dist_allgather_bytes(Ctx& c, const void* send_dev, size_t bytes_per_rank, void* recv_dev) {
+    if (c.nranks <= 1) { PORO_CUDA(cudaMemcpyAsync(recv_dev, send_dev, bytes_per_rank, cudaMemcpyDeviceToDevice, c.stream)); return; }
+    NCCL_OK(c.nccl, c.nccl->AllGather(send_dev, recv_dev, bytes_per_rank, NCCL_INT8, (ncclComm_p)c.comm, c.stream));
 }
 
 // ---- set-up primitives of the distributed hierarchy (distamg.cu): grouped byte send/recv, all-gather of int64 --------

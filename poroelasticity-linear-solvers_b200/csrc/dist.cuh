@@ -21,4 +21,7 @@ void dist_group_end(Ctx& c);
 void dist_send_bytes(Ctx& c, const void* dev, size_t bytes, int peer);
 void dist_recv_bytes(Ctx& c, void* dev, size_t bytes, int peer);
 void dist_allgather_i64(Ctx& c, const int64_t* mine, int count, std::vector<int64_t>& all);
+void dist_allgather_bytes(Ctx& c, const void* send_dev, size_t bytes_per_rank, void* recv_dev);
+// full[offs[r] .. offs[r+1]) = the slice of rank r, on every rank (peer stores when available, else a padded all-reduce)
+void dist_allgather_slices(Ctx& c, const double* mine, const std::vector<int64_t>& offs, double* full);
 }  // namespace poro
