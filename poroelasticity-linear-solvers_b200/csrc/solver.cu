@@ -67,13 +67,16 @@ void MatOp::apply(const double* x, double* y, SpmvMode mode, const double* z) {
     }
 }
 
+__global__ void __launch_bounds__(256) k_invert_diag(double* __restrict__ d, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) d[i] = d[i] != 0.0 ? 1.0 / d[i] : 1.0;
+}
+
 PCJacobi::PCJacobi(Ctx* c, const Csr& A) : ctx(c) {
     dinv.alloc((size_t)A.nrows);
     csr_diag(*c, A, dinv.p);
-    std::vector<double> h((size_t)A.nrows);
-    PORO_CUDA(cudaMemcpy(h.data(), dinv.p, h.size() * 8, cudaMemcpyDeviceToHost));
-    for (auto& v : h) v = v != 0.0 ? 1.0 / v : 1.0;
-    PORO_CUDA(cudaMemcpy(dinv.p, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+    if (A.nrows) k_invert_diag<<<ceil_div(A.nrows, 256), 256, 0, c->stream>>>(dinv.p, A.nrows);
+    PORO_LAUNCH_CHECK(*c);
 }
 
 PCDense::PCDense(Ctx* c, const Csr& A_) : ctx(c), n(A_.nrows) {
