@@ -458,7 +458,7 @@ void Amg::setup(Ctx& c, const Csr& A, int bs, const double* B_dev, int k, const 
         const int n_gh = dist ? Lp->plan->n_ghost : 0;
         const int64_t n_glob = dist ? Lp->plan->offsets.back() : n;
         if (dist && levels.size() >= 2 && !par.smoother_only && n_glob > par.coarse_size &&
-            n_glob <= c.opt_i("-poro_amg_replicate_below", 60000)) {
+            n_glob <= c.opt_i("-poro_amg_replicate_below", 0)) {
             // latency-bound level: gather it once, build and cycle the rest of the hierarchy redundantly on every rank
             Tick t(c, "gathered tail hierarchy");
             DBuf<double> Bg;

@@ -44,7 +44,9 @@ struct Amg {
     bool dist = false;
     // small distributed levels are latency-bound (6 halo exchanges per level visit): below `-poro_amg_replicate_below` global
     // rows a level is gathered ONCE at set-up, the rest of the hierarchy is built and cycled redundantly on every rank, and a
-    // cycle pays one all-gather of the level's right-hand side instead (oracle/distamg.py: replicate_below)
+    // cycle pays one all-gather of the level's right-hand side instead (oracle/distamg.py: replicate_below).  OFF by default:
+    // measured on 8 GPUs (N = 68) the redundant 20k-row solid level costs more than its six exchanges (259 vs 253 ms per solve),
+    // on 2 GPUs it gains 1.5 % (128.1 vs 130.3 ms); profiles/r2_scaling.md
     std::unique_ptr<Amg> tail;
     Csr tail_A;
     DBuf<double> tail_b, tail_x;
