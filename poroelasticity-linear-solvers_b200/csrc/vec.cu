@@ -7,6 +7,7 @@
 // tiny kernel that sums the per-block partials in a fixed order (deterministic results).
 #include "common.cuh"
 #include "dist.cuh"
+#include <algorithm>
 
 namespace poro {
 
@@ -149,14 +150,22 @@ void vec_dots(Ctx& c, int k, const double* const* xs, const double* const* ys, i
 static constexpr int kRpt = 4;     // rows per thread per tile
 static constexpr int kCchunk = 4;  // columns in flight
 
+// grid.y = chunks of kMc basis columns.  A thread keeps kMc running sums in registers over ALL its rows (kRpt rows x kMc
+// columns = 32 independent loads in flight) and the warp / block reduction happens ONCE at the end of the kernel -- the
+// first version reduced every 1024-row tile through shuffles and was shuffle-bound (3.1 TB/s at 18 columns).  w is re-read
+// once per column chunk (from L2: the chunks of one row range run concurrently).
+static constexpr int kMc = 8;
+
 __global__ void __launch_bounds__(kBlock) k_mdot(const double* __restrict__ V, int64_t ld, int ncol,
                                                  const double* __restrict__ w, int64_t n, bool with_ww,
                                                  double* __restrict__ partial) {
-    extern __shared__ double acc[];   // [kBlock/32][nout]
     const int nout = ncol + (with_ww ? 1 : 0);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int j = threadIdx.x; j < (kBlock / 32) * nout; j += kBlock) acc[j] = 0.0;
-    __syncthreads();
+    const int c0 = blockIdx.y * kMc;
+    const bool do_ww = with_ww && blockIdx.y == 0;
+    double s[kMc];
+#pragma unroll
+    for (int cc = 0; cc < kMc; ++cc) s[cc] = 0.0;
+    double sww = 0.0;
     const int64_t tile = (int64_t)kBlock * kRpt;
     for (int64_t base = (int64_t)blockIdx.x * tile; base < n; base += (int64_t)gridDim.x * tile) {
         double wv[kRpt];
@@ -166,38 +175,41 @@ __global__ void __launch_bounds__(kBlock) k_mdot(const double* __restrict__ V, i
             row[r] = base + (int64_t)r * kBlock + threadIdx.x;
             wv[r] = row[r] < n ? w[row[r]] : 0.0;
         }
-        if (with_ww) {
-            double s = 0.0;
+        double v[kMc][kRpt];
 #pragma unroll
-            for (int r = 0; r < kRpt; ++r) s = fma(wv[r], wv[r], s);
-            s = warp_sum(s);
-            if (lane == 0) acc[warp * nout + ncol] += s;
+        for (int cc = 0; cc < kMc; ++cc) {
+            const double* col = V + (int64_t)(c0 + cc) * ld;
+#pragma unroll
+            for (int r = 0; r < kRpt; ++r) v[cc][r] = (c0 + cc < ncol && row[r] < n) ? col[row[r]] : 0.0;
         }
-        for (int c0 = 0; c0 < ncol; c0 += kCchunk) {
-            double s[kCchunk];
 #pragma unroll
-            for (int cc = 0; cc < kCchunk; ++cc) {
-                s[cc] = 0.0;
-                if (c0 + cc < ncol) {
-                    const double* col = V + (int64_t)(c0 + cc) * ld;
+        for (int cc = 0; cc < kMc; ++cc) {
 #pragma unroll
-                    for (int r = 0; r < kRpt; ++r)
-                        if (row[r] < n) s[cc] = fma(col[row[r]], wv[r], s[cc]);
-                }
-            }
+            for (int r = 0; r < kRpt; ++r) s[cc] = fma(v[cc][r], wv[r], s[cc]);
+        }
+        if (do_ww) {
 #pragma unroll
-            for (int cc = 0; cc < kCchunk; ++cc) {
-                double t = warp_sum(s[cc]);
-                if (lane == 0 && c0 + cc < ncol) acc[warp * nout + c0 + cc] += t;
-            }
+            for (int r = 0; r < kRpt; ++r) sww = fma(wv[r], wv[r], sww);
         }
     }
+    __shared__ double sm[kBlock / 32][kMc + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int cc = 0; cc < kMc; ++cc) {
+        const double t = warp_sum(s[cc]);
+        if (lane == 0) sm[warp][cc] = t;
+    }
+    {
+        const double t = warp_sum(sww);
+        if (lane == 0) sm[warp][kMc] = t;
+    }
     __syncthreads();
-    for (int j = threadIdx.x; j < nout; j += kBlock) {
+    if (threadIdx.x <= kMc) {
         double t = 0.0;
 #pragma unroll
-        for (int wq = 0; wq < kBlock / 32; ++wq) t += acc[wq * nout + j];
-        partial[(size_t)blockIdx.x * nout + j] = t;
+        for (int wq = 0; wq < kBlock / 32; ++wq) t += sm[wq][threadIdx.x];
+        if (threadIdx.x < kMc) { if (c0 + (int)threadIdx.x < ncol) partial[(size_t)blockIdx.x * nout + c0 + threadIdx.x] = t; }
+        else if (do_ww) partial[(size_t)blockIdx.x * nout + ncol] = t;
     }
 }
 
@@ -207,9 +219,8 @@ void vec_mdot(Ctx& c, const double* V, int64_t ld, int ncol, const double* w, in
     int grid = stream_grid(c, n, kBlock, kRpt, 2);
     while ((int64_t)grid * nout > Ctx::kScal && grid > 1) grid /= 2;
     PORO_REQUIRE((int64_t)grid * nout <= Ctx::kScal, "mdot scratch too small");
-    size_t smem = (size_t)(kBlock / 32) * nout * sizeof(double);
-    PORO_REQUIRE(smem <= 48 * 1024, "too many basis columns for the multi-dot kernel");
-    k_mdot<<<grid, kBlock, smem, c.stream>>>(V, ld, ncol, w, n, with_ww, c.d_scal);
+    const int nchunk = std::max(1, (ncol + kMc - 1) / kMc);
+    k_mdot<<<dim3(grid, nchunk), kBlock, 0, c.stream>>>(V, ld, ncol, w, n, with_ww, c.d_scal);
     PORO_LAUNCH_CHECK(c);
     k_sum_partials<<<nout < 64 ? nout : 64, kBlock, 0, c.stream>>>(c.d_scal, grid, nout, d_h);
     PORO_LAUNCH_CHECK(c);
