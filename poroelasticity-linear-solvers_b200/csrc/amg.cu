@@ -426,6 +426,10 @@ void Amg::setup(Ctx& c, const Csr& A, int bs, const double* B_dev, int k, const 
     par = p;
     A0 = &A;
     levels.clear();
+    // opt-in: fp32 STORAGE of every operator of the hierarchy (level operators incl. the block itself, P, R); the V-cycle stays a
+    // fixed linear operator in fp64 arithmetic, so plain GMRES remains valid (profiles/r1_mixed_precision_study.md)
+    const bool fp32m = c.opt_i("-poro_pc_fp32_matrices", 0) != 0;
+    if (fp32m && A.bsr_state < 0) A.fp32_hint = true;
     DBuf<double> B;
     int n = A.nrows;
     if (B_dev) {
@@ -566,6 +570,7 @@ void Amg::setup(Ctx& c, const Csr& A, int bs, const double* B_dev, int k, const 
             Lp->P.block_hint = hint;
             Lp->R.block_hint = hint;
             Ac.block_hint = k;
+            Lp->P.fp32_hint = Lp->R.fp32_hint = Ac.fp32_hint = fp32m;
         }
         Anext = std::move(Ac);
         have_next = true;

@@ -28,9 +28,11 @@ static constexpr int kMaxBRows = 256;     // block rows per chunk (row pointers 
 //       multiplied instead of trailing the CTA (the tail that cost the Chebyshev-step launches 0.160 vs 0.135 ms).
 // FUSE: a mass coupling c M (x) I with the same block pattern rides along (one scalar per block in `mval`, a 3-bit row mask
 //       in the top bits of the column word): y = A x + C x2 in one pass.
-template <int BS, int MODE, bool DIAG, bool PREF, bool FUSE>
+// VT: storage type of the matrix values (double; float for the opt-in fp32 storage of preconditioner matrices -- every value
+//     is converted on load, all arithmetic and all vectors stay fp64)
+template <int BS, int MODE, bool DIAG, bool PREF, bool FUSE, typename VT = double>
 __global__ void __launch_bounds__(kBlk, FUSE ? 3 : 4) k_bsr_stream(const int4* __restrict__ desc, const int* __restrict__ rowptr,
-                                                     const int* __restrict__ col, const double* __restrict__ val,
+                                                     const int* __restrict__ col, const VT* __restrict__ val,
                                                      const double* __restrict__ mval, const double* __restrict__ x,
                                                      const double* __restrict__ x2, double* __restrict__ y, Epilogue ep,
                                                      double* __restrict__ dot_partial, int G) {
@@ -73,9 +75,9 @@ __global__ void __launch_bounds__(kBlk, FUSE ? 3 : 4) k_bsr_stream(const int4* _
 #pragma unroll
     for (int t = 0; t < kNtb; ++t) {
         const int p = p0 + threadIdx.x + t * kBlk;
-        const double* vb = val + ((size_t)(p >> 5) * NE) * 32 + (p & 31);
+        const VT* vb = val + ((size_t)(p >> 5) * NE) * 32 + (p & 31);
 #pragma unroll
-        for (int e = 0; e < NE; ++e) v[t][e] = c[t] >= 0 ? __ldcs(vb + e * 32) : 0.0;
+        for (int e = 0; e < NE; ++e) v[t][e] = c[t] >= 0 ? (double)__ldcs(vb + e * 32) : 0.0;
     }
     for (int i = threadIdx.x; i <= nbr; i += kBlk) rp[i] = rowptr[R0 + i];     // needed after the barrier only
 #pragma unroll
@@ -272,6 +274,17 @@ bool bsr_from_csr(Ctx& c, const Csr& A, int BS, Bsr& out, double max_fill) {
         PORO_CUDA(cudaStreamSynchronize(c.stream));
     }
     PORO_CUDA(cudaStreamSynchronize(c.stream));
+    if (A.fp32_hint) {
+        // opt-in fp32 storage: 4 NE + 4 instead of 8 NE + 4 bytes per block; converted once, the fp64 copy is dropped
+        const size_t nv = out.val.n;
+        out.val32.alloc(nv);
+        const double* src = out.val.p; float* dst = out.val32.p;
+        pfor(c, (int64_t)nv, [=] __device__(int64_t i) { dst[i] = (float)src[i]; });
+        PORO_CUDA(cudaStreamSynchronize(c.stream));
+        out.val.release();
+        out.fp32 = true;
+        return true;
+    }
     // Blackwell path: chunked layout for the persistent TMA kernel; the plain arrays are only kept when it is unavailable
     if (c.opt_i("-poro_bsr_tma", 0) && bsr_build_tma(c, out, rp)) {
         out.val.release();
@@ -342,8 +355,15 @@ int bsr_launch(Ctx& c, const Bsr& B, const double* x, double* y, const Epilogue&
     const double a = B.nbrows ? (double)B.nnzb / B.nbrows : 0.0;
     const int G = a <= 1.5 ? 1 : a <= 4 ? 2 : a <= 12 ? 4 : a <= 48 ? 8 : a <= 160 ? 16 : 32;
     const bool fuse = x2 != nullptr && B.fused;
-#define GO(BSS, DG, PF, FS) k_bsr_stream<BSS, MODE, DG, PF, FS><<<B.nblk, kBlk, 0, c.stream>>>(reinterpret_cast<const int4*>(B.blk_desc.p), B.rowptr.p, FS ? B.f_col.p : B.col.p, \
-                                B.val.p, FS ? B.f_m.p : nullptr, x, x2, y, ep, dot_partial, G)
+#define GO(BSS, DG, PF, FS)                                                                                                     \
+    do {                                                                                                                       \
+        if (B.fp32 && !FS)                                                                                                     \
+            k_bsr_stream<BSS, MODE, DG, PF, false, float><<<B.nblk, kBlk, 0, c.stream>>>(reinterpret_cast<const int4*>(B.blk_desc.p), B.rowptr.p, \
+                                B.col.p, B.val32.p, nullptr, x, x2, y, ep, dot_partial, G);                                     \
+        else                                                                                                                   \
+            k_bsr_stream<BSS, MODE, DG, PF, FS><<<B.nblk, kBlk, 0, c.stream>>>(reinterpret_cast<const int4*>(B.blk_desc.p), B.rowptr.p, FS ? B.f_col.p : B.col.p, \
+                                B.val.p, FS ? B.f_m.p : nullptr, x, x2, y, ep, dot_partial, G);                                 \
+    } while (0)
 #define GOB(BSS)                                                                                   \
     do {                                                                                           \
         if (fuse) { if (B.pref) GO(BSS, false, true, true); else GO(BSS, false, false, true); }     \

@@ -740,7 +740,7 @@ int poro_pc_block_bytes(poro_pc* pc, const char* name, int64_t* bytes, int* form
     if (B.bsr_state == 1) {
         const Bsr& b = *B.bsr;
         const int64_t ne = b.diag_only ? b.bs : b.bs * b.bs;
-        *bytes = (8 * ne + 4) * b.nnzb + 4 * ((int64_t)b.nbrows + 1) + 8 * (int64_t)B.nrows + 8 * (int64_t)B.ncols;
+        *bytes = ((b.fp32 ? 4 : 8) * ne + 4) * b.nnzb + 4 * ((int64_t)b.nbrows + 1) + 8 * (int64_t)B.nrows + 8 * (int64_t)B.ncols;
         *format = b.diag_only ? 2 : 1;
     } else {
         *bytes = 12 * B.nnz + 4 * ((int64_t)B.nrows + 1) + 8 * (int64_t)B.nrows + 8 * (int64_t)B.ncols;

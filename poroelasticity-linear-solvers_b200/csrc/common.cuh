@@ -212,6 +212,8 @@ struct Bsr {
     bool diag_only = false;     // blocks are diagonal (e.g. M (x) I couplings): BS values per block instead of BS^2
     DBuf<int> rowptr, col;
     DBuf<double> val;
+    DBuf<float> val32;          // optional fp32 STORAGE of the values (arithmetic stays fp64), `-poro_pc_fp32_matrices`
+    bool fp32 = false;
     DBuf<int> blk_row, blk_desc;    // chunk boundaries; per chunk {first block row, block rows, first block, blocks}
     int nblk = 0;
     bool pref = false;          // every chunk has <= 256 scalar rows: epilogue operands are prefetched (k_bsr_stream PREF)
@@ -239,6 +241,7 @@ struct Csr {
     mutable DBuf<int> blk_row;
     // node-block size hint (dofs per mesh node); > 1 makes the first product try a BSR conversion
     int block_hint = 0;
+    mutable bool fp32_hint = false;             // store the BSR values in fp32 (preconditioner matrices only, opt-in)
     mutable int bsr_state = -1;                 // -1 not tried, 0 rejected (fill-in / shape), 1 in use
     mutable std::shared_ptr<Bsr> bsr;
     double avg_row() const { return nrows ? (double)nnz / nrows : 0.0; }

@@ -240,3 +240,21 @@ def test_single_block_drivers(gpu_ctx, block):
     assert np.linalg.norm(rhs - M @ x) / np.linalg.norm(rhs) <= 1e-7
     assert rel(x, xd) <= 1e-5
     gpu_ctx.set_halo(0, [], [0], [], [])
+
+
+def test_fp32_storage_of_preconditioner_matrices_is_only_a_preconditioner_change(gpu_ctx):
+    """Opt-in `-poro_pc_fp32_matrices 1`: the hierarchies' operators are STORED in fp32 (arithmetic, vectors and the outer operator
+    stay fp64).  The preconditioner remains a fixed linear operator, so GMRES converges to the same solution; only the iteration
+    count may move by a step."""
+    import bench
+    from oracle.problems import swelling
+    sys_, par = swelling(3, 8, "diagonal")
+    par = dict(par)
+    par.update({"solver rtol": 1e-10, "solver atol": 0.0, "solver maxiter": 100, "solver type": "gmres"})
+    g64 = gpu_solve(sys_, par, bench.BENCH_OPTIONS)
+    g32 = gpu_solve(sys_, par, bench.BENCH_OPTIONS + "\n-poro_pc_fp32_matrices 1\n")
+    assert g64["reason"] == 2 and g32["reason"] == 2
+    assert abs(g32["its"] - g64["its"]) <= 2
+    res = np.linalg.norm(sys_.b - sys_.A @ g32["x"]) / np.linalg.norm(sys_.b)
+    assert res <= 1.01e-10
+    assert rel(g32["x"], g64["x"]) <= 1e-8
