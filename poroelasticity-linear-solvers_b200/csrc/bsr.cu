@@ -30,14 +30,48 @@ static constexpr int kMaxBRows = 256;     // block rows per chunk (row pointers 
 //       in the top bits of the column word): y = A x + C x2 in one pass.
 // VT: storage type of the matrix values (double; float for the opt-in fp32 storage of preconditioner matrices -- every value
 //     is converted on load, all arithmetic and all vectors stay fp64)
-template <int BS, int MODE, bool DIAG, bool PREF, bool FUSE, typename VT = double>
+// L2 prefetch (pf.groups > 0): the kernel is bound by its exposed DRAM latencies, not by a pipe (ncu: LSU 21 %, L1 wavefronts
+//     55 %, issue 24 %; storing the values in fp32 moved 43 % fewer bytes in the SAME time).  One lane per CTA therefore asks
+//     the TMA unit to pull the value / column / operand ranges of the chunk `pf.groups` groups further down the stream into
+//     L2 (cp.async.bulk.prefetch.L2): consecutive chunks tile the arrays, so the shifted ranges tile them too, and by the
+//     time that chunk's CTA is scheduled its loads are L2 hits.
+struct BsrPrefetch {
+    int groups;       // distance in groups of 32 blocks
+    int ngroups;      // groups in the matrix (clip)
+    int rows;         // distance in scalar rows
+    int nrows;        // scalar rows (clip)
+};
+__device__ __forceinline__ void l2_prefetch(const void* p, unsigned bytes, bool evict_first = false) {
+    if (evict_first) {
+        // the matrix stream must not displace the gathered vectors from L2 (the demand loads are ld.global.cs for the same reason)
+        unsigned long long pol;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+        asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(p), "r"(bytes), "l"(pol) : "memory");
+    } else {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+    }
+}
+// [lo, hi) in elements of `esz` bytes, widened to 16-byte boundaries (the arrays are allocated in 256-byte units)
+__device__ __forceinline__ void l2_prefetch_range(const void* base, long long lo, long long hi, int esz, bool evict_first = false) {
+    const unsigned long long a = ((unsigned long long)base + (unsigned long long)lo * esz) & ~15ull;
+    const unsigned long long b = ((unsigned long long)base + (unsigned long long)hi * esz + 15ull) & ~15ull;
+    if (b > a) l2_prefetch((const void*)a, (unsigned)(b - a), evict_first);
+}
+// COOP: the 32 x BS doubles of x a warp needs are gathered by (block, component) pairs laid out lane-contiguously -- lane l of
+//     load k fetches component (32k + l) % BS of block (32k + l) / BS -- and handed to their owners through the warp's own
+//     slice of `part`.  Thread-per-block gathers touch up to 32 nodes (~12 cache lines) per load instruction, and the L1
+//     wavefront queue, not DRAM, is what the kernel saturates (ncu: 176 k wavefronts per SM in 313 k cycles at ~2 cycles per
+//     replayed wavefront); the cooperative form touches 32 / BS nodes per instruction.
+template <int BS, int MODE, bool DIAG, bool PREF, bool FUSE, typename VT = double, bool COOP = false>
 __global__ void __launch_bounds__(kBlk, FUSE ? 3 : 4) k_bsr_stream(const int4* __restrict__ desc, const int* __restrict__ rowptr,
                                                      const int* __restrict__ col, const VT* __restrict__ val,
                                                      const double* __restrict__ mval, const double* __restrict__ x,
                                                      const double* __restrict__ x2, double* __restrict__ y, Epilogue ep,
-                                                     double* __restrict__ dot_partial, int G) {
+                                                     double* __restrict__ dot_partial, int G, BsrPrefetch pf) {
     constexpr int kNtb = 2;
     __shared__ double part[kBlk * kNtb * BS];
+    __shared__ double part2[(COOP && FUSE) ? kBlk * kNtb * BS : 1];
+    __shared__ double eop[(COOP && PREF && MODE == 3) ? 2 * kBlk : 1];      // D^-1 and x of the Chebyshev step wait here, not in registers
     __shared__ double rsum[kMaxBRows * BS];
     __shared__ int rp[kMaxBRows + 1];
     __shared__ double red[kBlk / 32];
@@ -51,8 +85,34 @@ __global__ void __launch_bounds__(kBlk, FUSE ? 3 : 4) k_bsr_stream(const int4* _
     double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
     if (has_row) {
         if (MODE == SPMV_SUB || MODE == SPMV_ADD) e0 = ep.z[myrow];
+        else if (MODE == 3 && COOP) {
+            e0 = ep.r[myrow]; e1 = ep.d_old[myrow];
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(eop + threadIdx.x)), "l"(ep.dinv + myrow) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(eop + kBlk + threadIdx.x)), "l"(ep.xv + myrow) : "memory");
+        }
         else if (MODE == 3) { e0 = ep.r[myrow]; e1 = ep.d_old[myrow]; e2 = ep.dinv[myrow]; e3 = ep.xv[myrow]; }
         else if (MODE == 4) e0 = x[myrow];
+    }
+    if (pf.groups > 0 && threadIdx.x == kBlk - 32) {
+        constexpr int NEs = DIAG ? BS : BS * BS;
+        const int g0 = (p0 >> 5) + pf.groups, g1 = min(((p0 + cnt) >> 5) + pf.groups, pf.ngroups);
+        if (g1 > g0) {
+            l2_prefetch(val + (size_t)g0 * NEs * 32, (unsigned)((g1 - g0) * NEs * 32 * (int)sizeof(VT)), true);
+            l2_prefetch_range(col, (long long)g0 * 32, (long long)g1 * 32, 4, true);
+            if (FUSE) l2_prefetch_range(mval, (long long)g0 * 32, (long long)g1 * 32, 8, true);
+        }
+        if (PREF && MODE != SPMV_SET) {
+            const long long r0 = (long long)R0 * BS + pf.rows, r1 = min((long long)(R0 + nbr) * BS + pf.rows, (long long)pf.nrows);
+            if (r1 > r0) {
+                if (MODE == SPMV_SUB || MODE == SPMV_ADD) l2_prefetch_range(ep.z, r0, r1, 8);
+                else if (MODE == 3) {
+                    l2_prefetch_range(ep.r, r0, r1, 8);
+                    l2_prefetch_range(ep.d_old, r0, r1, 8);
+                    l2_prefetch_range(ep.dinv, r0, r1, 8);
+                    l2_prefetch_range(ep.xv, r0, r1, 8);
+                }
+            }
+        }
     }
     // phase 1: one thread per block
     int c[kNtb];
@@ -80,16 +140,45 @@ __global__ void __launch_bounds__(kBlk, FUSE ? 3 : 4) k_bsr_stream(const int4* _
         for (int e = 0; e < NE; ++e) v[t][e] = c[t] >= 0 ? (double)__ldcs(vb + e * 32) : 0.0;
     }
     for (int i = threadIdx.x; i <= nbr; i += kBlk) rp[i] = rowptr[R0 + i];     // needed after the barrier only
+    if (COOP) {
+        const int ln = threadIdx.x & 31;
+        // global -> shared without a register stop (LDGSTS): all kNtb * BS gathers of the warp are in flight at once and cost
+        // no registers; a source size of 0 zero-fills the slots of absent blocks
+#pragma unroll
+        for (int t = 0; t < kNtb; ++t) {
+            double* st = part + ((threadIdx.x & ~31) + t * kBlk) * BS;       // this warp's slice for its blocks of round t
+            double* st2 = part2 + ((COOP && FUSE) ? ((threadIdx.x & ~31) + t * kBlk) * BS : 0);
+#pragma unroll
+            for (int k = 0; k < BS; ++k) {
+                const int q = 32 * k + ln;
+                const int bsrc = q / BS, j = q - bsrc * BS;
+                const int cc = __shfl_sync(0xffffffffu, c[t], bsrc);
+                const size_t off = cc >= 0 ? (size_t)cc * BS + j : 0;
+                const unsigned sz = cc >= 0 ? 8u : 0u;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((unsigned)__cvta_generic_to_shared(st + q)), "l"(x + off), "r"(sz) : "memory");
+                if (FUSE)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((unsigned)__cvta_generic_to_shared(st2 + q)), "l"(x2 + off), "r"(sz) : "memory");
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        // each thread reads and then overwrites below only the BS slots of its own blocks
+    }
 #pragma unroll
     for (int t = 0; t < kNtb; ++t) {
         const int i = threadIdx.x + t * kBlk;
         if (c[t] >= 0) {
             double xv[BS], x2v[BS];
+            if (COOP) {
 #pragma unroll
-            for (int j = 0; j < BS; ++j) xv[j] = __ldg(x + (size_t)c[t] * BS + j);
-            if (FUSE) {
+                for (int j = 0; j < BS; ++j) { xv[j] = part[i * BS + j]; if (FUSE) x2v[j] = part2[i * BS + j]; }
+            } else {
 #pragma unroll
-                for (int j = 0; j < BS; ++j) x2v[j] = __ldg(x2 + (size_t)c[t] * BS + j);
+                for (int j = 0; j < BS; ++j) xv[j] = __ldg(x + (size_t)c[t] * BS + j);
+                if (FUSE) {
+#pragma unroll
+                    for (int j = 0; j < BS; ++j) x2v[j] = __ldg(x2 + (size_t)c[t] * BS + j);
+                }
             }
 #pragma unroll
             for (int k = 0; k < BS; ++k) {
@@ -137,6 +226,7 @@ __global__ void __launch_bounds__(kBlk, FUSE ? 3 : 4) k_bsr_stream(const int4* _
             else if (MODE == SPMV_SUB) y[myrow] = e0 - sum;
             else if (MODE == SPMV_ADD) y[myrow] = e0 + sum;
             else if (MODE == 3) {
+                if (COOP) { e2 = eop[threadIdx.x]; e3 = eop[kBlk + threadIdx.x]; }      // own slots, completed by cp.async.wait_all above
                 const double rn = e0 - sum;
                 const double dn = ep.c1 * e1 + ep.c2 * e2 * rn;
                 ep.r[myrow] = rn;
@@ -247,6 +337,16 @@ bool bsr_from_csr(Ctx& c, const Csr& A, int BS, Bsr& out, double max_fill) {
     const bool pref = (double)nnzb >= 6.0 * nbr && c.opt_i("-poro_bsr_prefetch", 1) != 0;
     const int max_rows = pref ? kBlk / BS : kMaxBRows;
     out.pref = pref;
+    out.coop = c.opt_i("-poro_bsr_coop_gather", 0) != 0;
+    {
+        // L2 prefetch distance in chunks (0 = off): further than the 4 x SM-count resident CTAs, short of what L2 holds
+        const int64_t chunks = c.opt_i("-poro_bsr_l2_prefetch_chunks", 0);
+        const int64_t total_chunks = (nnzb + kBlk * out.ntb - 1) / (kBlk * out.ntb);
+        if (chunks > 0 && total_chunks > 2 * chunks) {
+            out.pf_groups = (int)(chunks * (kBlk * out.ntb / 32));
+            out.pf_rows = (int)((double)chunks * kBlk * out.ntb * nbr * BS / (double)nnzb) & ~1;
+        }
+    }
     std::vector<int> blk;
     int r = 0;
     while (r < nbr) {
@@ -355,14 +455,18 @@ int bsr_launch(Ctx& c, const Bsr& B, const double* x, double* y, const Epilogue&
     const double a = B.nbrows ? (double)B.nnzb / B.nbrows : 0.0;
     const int G = a <= 1.5 ? 1 : a <= 4 ? 2 : a <= 12 ? 4 : a <= 48 ? 8 : a <= 160 ? 16 : 32;
     const bool fuse = x2 != nullptr && B.fused;
+    const BsrPrefetch pf{B.pf_groups, (int)(B.nnzb >> 5), B.pf_rows, B.nbrows * B.bs};
 #define GO(BSS, DG, PF, FS)                                                                                                     \
     do {                                                                                                                       \
-        if (B.fp32 && !FS)                                                                                                     \
+        if (B.coop && !B.fp32)                                                                                                 \
+            k_bsr_stream<BSS, MODE, DG, PF, FS, double, true><<<B.nblk, kBlk, 0, c.stream>>>(reinterpret_cast<const int4*>(B.blk_desc.p), B.rowptr.p, FS ? B.f_col.p : B.col.p, \
+                                B.val.p, FS ? B.f_m.p : nullptr, x, x2, y, ep, dot_partial, G, pf);                             \
+        else if (B.fp32 && !FS)                                                                                                \
             k_bsr_stream<BSS, MODE, DG, PF, false, float><<<B.nblk, kBlk, 0, c.stream>>>(reinterpret_cast<const int4*>(B.blk_desc.p), B.rowptr.p, \
-                                B.col.p, B.val32.p, nullptr, x, x2, y, ep, dot_partial, G);                                     \
+                                B.col.p, B.val32.p, nullptr, x, x2, y, ep, dot_partial, G, pf);                                     \
         else                                                                                                                   \
             k_bsr_stream<BSS, MODE, DG, PF, FS><<<B.nblk, kBlk, 0, c.stream>>>(reinterpret_cast<const int4*>(B.blk_desc.p), B.rowptr.p, FS ? B.f_col.p : B.col.p, \
-                                B.val.p, FS ? B.f_m.p : nullptr, x, x2, y, ep, dot_partial, G);                                 \
+                                B.val.p, FS ? B.f_m.p : nullptr, x, x2, y, ep, dot_partial, G, pf);                                 \
     } while (0)
 #define GOB(BSS)                                                                                   \
     do {                                                                                           \

@@ -217,6 +217,9 @@ struct Bsr {
     DBuf<int> blk_row, blk_desc;    // chunk boundaries; per chunk {first block row, block rows, first block, blocks}
     int nblk = 0;
     bool pref = false;          // every chunk has <= 256 scalar rows: epilogue operands are prefetched (k_bsr_stream PREF)
+    bool coop = false;          // cooperative (lane-contiguous) gathers of x, see k_bsr_stream COOP
+    int pf_groups = 0;          // L2 prefetch distance of the stream kernel in groups of 32 blocks (0 = off), see bsr.cu
+    int pf_rows = 0;            // the same distance in scalar rows (epilogue operands)
     bool fused = false;         // a mass coupling rides along (plain layout): one scalar per block + row mask in the column word
     DBuf<double> f_m;
     DBuf<int> f_col;

@@ -28,6 +28,9 @@ out = {"N": N, "n": n, "nnzb": int(nnzb), "peak": peak, "rows": []}
 VARIANTS = [("ld.global.cs (bsr.cu)", {"-poro_bsr_tma": 0}), ("TMA 512x2, 2 CTA/SM", {"-poro_bsr_tma": 1, "-poro_bsr_tma_cfg": 0}),
             ("TMA 256x2, 4 CTA/SM", {"-poro_bsr_tma": 1, "-poro_bsr_tma_cfg": 1}), ("TMA 256x3, 3 CTA/SM", {"-poro_bsr_tma": 1, "-poro_bsr_tma_cfg": 2}),
             ("ld.global.cs, no operand prefetch", {"-poro_bsr_tma": 0, "-poro_bsr_prefetch": 0})]
+VARIANTS += [("ld.global.cs + L2 prefetch %d chunks ahead" % d, {"-poro_bsr_tma": 0, "-poro_bsr_l2_prefetch_chunks": d})
+             for d in (740, 1184, 1776, 2368, 4736, 640, 888)]
+VARIANTS += [("ld.global.cs + cooperative gathers", {"-poro_bsr_tma": 0, "-poro_bsr_coop_gather": 1})]      # index 12
 if os.environ.get("PROBE_VARIANTS"):
     VARIANTS = [VARIANTS[int(i)] for i in os.environ["PROBE_VARIANTS"].split(",")]
 if os.environ.get("PROBE_MODES"):

@@ -258,3 +258,19 @@ def test_fp32_storage_of_preconditioner_matrices_is_only_a_preconditioner_change
     res = np.linalg.norm(sys_.b - sys_.A @ g32["x"]) / np.linalg.norm(sys_.b)
     assert res <= 1.01e-10
     assert rel(g32["x"], g64["x"]) <= 1e-8
+
+
+@pytest.mark.parametrize("extra", ["-poro_bsr_coop_gather 1", "-poro_bsr_l2_prefetch_chunks 4", "-poro_bsr_tma 1"])
+def test_optional_bsr_kernel_variants_are_the_same_operator(gpu_ctx, extra):
+    """The measured-and-rejected kernel variants (profiles/r2_bsr_kernels.md) stay selectable; they must be the same linear
+    operators as the default kernel: same iteration count, same solution."""
+    import bench
+    from oracle.problems import swelling
+    sys_, par = swelling(3, 8, "diagonal")
+    par = dict(par)
+    par.update({"solver rtol": 1e-10, "solver atol": 0.0, "solver maxiter": 100, "solver type": "gmres"})
+    ref = gpu_solve(sys_, par, bench.BENCH_OPTIONS)
+    alt = gpu_solve(sys_, par, bench.BENCH_OPTIONS + "\n" + extra + "\n")
+    assert alt["reason"] == ref["reason"] == 2
+    assert alt["its"] == ref["its"]
+    assert rel(alt["x"], ref["x"]) <= 1e-10
