@@ -6,8 +6,8 @@ throughput, SpMV HBM roofline.
 
 A "step" is ONE complete `Solver.solve(b, x)` of the assembled three-field system from a zero
 initial guess to relative residual 1e-8 (right-preconditioned GMRES + block `diagonal`
-preconditioner: one SA-AMG V-cycle on the solid block, Chebyshev(4) on the mass-dominated fluid block,
-one V-cycle on the selfp pressure Schur complement) -- set-up (assembly, upload,
+preconditioner: one SA-AMG V-cycle on the solid block, one on the fluid-velocity block, and the additive
+Cahouet-Chabard pressure Schur preconditioner: one V-cycle on the lumped-mass Schur complement + Chebyshev(4) on the pressure mass matrix) -- set-up (assembly, upload,
 AMG hierarchy) is outside the timed region exactly as the reference times only `ksp.solve`
 (lib/Solver.py:148-152).  `value` = DoFs solved to 1e-8 per second = n_dofs / time-to-1e-8 over the K
 timed steps (whole job, all ranks; a weaker preconditioner that needs more iterations scores LOWER);
@@ -51,14 +51,25 @@ BENCH_OPTIONS = """
 -fp_ksp_type preonly
 -fp_pc_fieldsplit_type schur
 -fp_pc_fieldsplit_schur_fact_type lower
--fp_pc_fieldsplit_schur_precondition selfp
+-fp_pc_fieldsplit_schur_precondition cc
 -fp_pc_fieldsplit_order fp
 -fp_fieldsplit_0_ksp_type preonly
--fp_fieldsplit_0_pc_type chebyshev
+-fp_fieldsplit_0_pc_type hypre
+-fp_fieldsplit_0_pc_amg_theta 0.04
+-fp_fieldsplit_0_pc_amg_coarse_size 6000
 -fp_fieldsplit_1_ksp_type preonly
 -fp_fieldsplit_1_pc_type hypre
 -fp_fieldsplit_1_pc_amg_coarse_size 6000
 """
+# `-fp_pc_fieldsplit_schur_precondition cc`: the additive Cahouet-Chabard form of the pressure Schur preconditioner -- the pressure
+# treatment of the reference's 3-way variants (beta_CC1 / beta_CC2, lib/Assembler.py:131-137) inside the 2-way fieldsplit -- with a
+# V-cycle on the velocity block.  PETSc's `selfp` (the set benchmarked until the middle of round 2, kept below and parity-tested)
+# loses mesh independence once the viscous part of P_ff overtakes its mass + drag part: 36 / 44 / 55 / 70 / 109 iterations at
+# N = 34 / 43 / 54 / 68 / 101 against 27 / 29 / ... with `cc` (profiles/r2_schur_cc.md).
+BENCH_OPTIONS_SELFP = (BENCH_OPTIONS.replace("-fp_pc_fieldsplit_schur_precondition cc", "-fp_pc_fieldsplit_schur_precondition selfp")
+                       .replace("-fp_fieldsplit_0_pc_type hypre\n-fp_fieldsplit_0_pc_amg_theta 0.04\n-fp_fieldsplit_0_pc_amg_coarse_size 6000\n",
+                                "-fp_fieldsplit_0_pc_type chebyshev\n"))
+BENCH_OPTIONS_CC = BENCH_OPTIONS
 PHASE_NAMES = {0: "outer_A_apply", 1: "pc_apply", 2: "s_solve", 3: "fp_split0(f)", 4: "fp_split1(p)", 5: "gram_schmidt",
                6: "fp_coupling", **{8 + l: "s_amg_L%d" % l for l in range(8)}, **{16 + l: "f_amg_L%d" % l for l in range(8)},
                **{24 + l: "p_amg_L%d" % l for l in range(8)}, 32: "A_remainder_csr", 33: "A_part0", 34: "A_part1", 35: "A_part2", 36: "A_part3",
@@ -66,6 +77,12 @@ PHASE_NAMES = {0: "outer_A_apply", 1: "pc_apply", 2: "s_solve", 3: "fp_split0(f)
 RTOL = 1e-8
 METRIC = "3D swelling (swelling-3d.py) solve to rtol 1e-8: DoFs solved per second (n_dofs / time-to-1e-8)"
 UNIT = "DoF/s"
+
+
+def active_options() -> str:
+    """The option text of this run: BENCH_OPTIONS plus the A/B switches of PORO_EXTRA_OPTIONS (later keys win)."""
+    extra = os.environ.get("PORO_EXTRA_OPTIONS", "").strip()
+    return BENCH_OPTIONS + ("\n" + extra.replace(";", "\n") + "\n" if extra else "")
 
 
 def mesh_for_gpus(base_n: int, gpus: int) -> int:
@@ -119,22 +136,39 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def oracle_solver(sys_, par, max_it):
-    """The CPU port of the benchmarked algorithm (same options as BENCH_OPTIONS).
+def oracle_solver(sys_, par, max_it, options_text=None):
+    """The CPU port of the benchmarked algorithm (same options as BENCH_OPTIONS, or as `options_text`: the selfp / cc
+    Schur preconditioner and the Chebyshev / V-cycle choice on the velocity block are read from it).
 
     Returns {label: (run, cores)}: the numpy/scipy oracle on one thread, and the same preconditioner handed
     to the C + OpenMP solve loop (oracle/csrc/cpu_solver.c) with the thread count that is fastest on this host."""
     from oracle.amg import SAAMG, rigid_body_modes
-    from oracle.blockpc import BlockPC, SchurLower, krylov_solver
+    from oracle.blockpc import BlockPC, SchurLower, SchurLowerCC, cc_from_matrices, krylov_solver
     from oracle.krylov import gmres
     from oracle import cport
+    opts = {}
+    for line in (options_text if options_text is not None else active_options()).splitlines():
+        w = line.split()
+        if w and not w[0].startswith("#"):
+            opts[w[0].lstrip("-")] = w[-1] if len(w) > 1 else None
     dim = sys_.dim
     B = rigid_body_modes(sys_.coords_s, dim)
     # coarsening stops below 6 000 (global) rows, where one dense inverse is cheaper than further latency-bound levels
     amg_s = lambda M: SAAMG(M, dim, B, theta=0.04, coarse_size=6000, dense_limit=8192)   # -s_pc_amg_theta 0.04 -s_pc_amg_coarse_size 6000
     cheb_f = lambda M: SAAMG(M, dim, B, max_levels=1, cheby_degree=4, dense_limit=0)   # -fp_fieldsplit_0_pc_type chebyshev
     amg_p = lambda M: SAAMG(M, 1, None, coarse_size=6000, dense_limit=8192)
-    mkfp = lambda M: SchurLower(M, sys_.nf, sys_.np_, krylov_solver("preonly", cheb_f), krylov_solver("preonly", amg_p), "f")
+    k_f = cheb_f
+    if opts.get("fp_fieldsplit_0_pc_type", "chebyshev") != "chebyshev":
+        # -fp_fieldsplit_0_pc_type hypre -fp_fieldsplit_0_pc_amg_theta .. -fp_fieldsplit_0_pc_amg_coarse_size ..
+        k_f = lambda M: SAAMG(M, dim, B, theta=float(opts.get("fp_fieldsplit_0_pc_amg_theta", 0.08)),
+                              coarse_size=int(opts.get("fp_fieldsplit_0_pc_amg_coarse_size", 400)), dense_limit=8192)
+    if opts.get("fp_pc_fieldsplit_schur_precondition", "selfp") == "cc":
+        d_mass, S_visc = cc_from_matrices(sys_, par)
+        cheb_p = lambda M: SAAMG(M, 1, None, max_levels=1, cheby_degree=4, dense_limit=0)
+        mkfp = lambda M: SchurLowerCC(M, sys_.nf, sys_.np_, krylov_solver("preonly", k_f), krylov_solver("preonly", amg_p),
+                                      krylov_solver("preonly", cheb_p), d_mass, S_visc)
+    else:
+        mkfp = lambda M: SchurLower(M, sys_.nf, sys_.np_, krylov_solver("preonly", k_f), krylov_solver("preonly", amg_p), "f")
     pc = BlockPC(sys_, {"s": krylov_solver("preonly", amg_s), "fp": mkfp})
     A = sys_.A
 
@@ -250,8 +284,9 @@ def run_reference(args):
 
 def workload_text(N, n_global, nnzA, maxiter, restart, world):
     return ("swelling-3d.py -N %d (%d DoFs, nnz(A)=%d on rank 0), GMRES(right, maxiter=%d, restart=%s) + block 'diagonal' 2-way PC: "
-            "SA-AMG V-cycle (s), Chebyshev(4) (f), V-cycle on the selfp pressure Schur complement (p); rtol 1e-8, zero initial "
-            "guess" % (N, n_global, nnzA, maxiter, restart))
+            "SA-AMG V-cycle (s), SA-AMG V-cycle (f), additive Cahouet-Chabard pressure Schur preconditioner (V-cycle on P_pp - P_pf "
+            "diag(c M_v)^-1 P_fp + Chebyshev(4) on the pressure mass matrix); rtol 1e-8, zero initial guess"
+            % (N, n_global, nnzA, maxiter, restart))
 
 
 def measured_traffic(kernel_key: str, bytes_per_launch: int):

@@ -45,7 +45,7 @@ class _Amg(C.Structure):
 
 class _BlockPC(C.Structure):
     _fields_ = [("ns", C.c_int64), ("nf", C.c_int64), ("np", C.c_int64), ("Ks", C.POINTER(_Amg)),
-                ("Kf", C.POINTER(_Amg)), ("Kp", C.POINTER(_Amg)), ("Mfps", _Csr), ("Apf", _Csr)]
+                ("Kf", C.POINTER(_Amg)), ("Kp", C.POINTER(_Amg)), ("Mfps", _Csr), ("Apf", _Csr), ("Kv", C.POINTER(_Amg))]
 
 
 def lib():
@@ -136,9 +136,11 @@ class CSolver:
         if pc.three_way or pc.anderson is not None:
             raise ValueError("C port covers the 2-way preconditioner without Anderson acceleration")
         fp = pc.k_fp
-        if getattr(fp, "first", None) != "f":
+        cc = hasattr(fp, "k_visc")              # oracle.blockpc.SchurLowerCC (velocity first by construction)
+        if not cc and getattr(fp, "first", None) != "f":
             raise ValueError("C port covers the pressure-Schur split (first='f')")
-        for k in (pc.k_s, fp.k0, fp.k1):
+        k1 = fp.k_mass if cc else fp.k1
+        for k in (pc.k_s, fp.k0, k1) + ((fp.k_visc,) if cc else ()):
             if k.type != "preonly":
                 raise ValueError("C port covers preonly inner solves")
         self.keep = _Keep()
@@ -146,9 +148,11 @@ class CSolver:
         self.perm = np.concatenate([sys_.is_s, sys_.is_fp])
         A = sp.csr_matrix(sys_.A)[self.perm][:, self.perm].tocsr()
         self.A = self.keep.csr(A)
-        self.ks, self.kf, self.kp = CAmg(pc.k_s.M), CAmg(fp.k0.M), CAmg(fp.k1.M)
+        self.ks, self.kf, self.kp = CAmg(pc.k_s.M), CAmg(fp.k0.M), CAmg(k1.M)
+        self.kv = CAmg(fp.k_visc.M) if cc else None
         self.pc = _BlockPC(len(sys_.is_s), fp.nf, fp.np_, C.pointer(self.ks.h), C.pointer(self.kf.h),
-                           C.pointer(self.kp.h), self.keep.csr(pc.Mfp_s), self.keep.csr(fp.A10))
+                           C.pointer(self.kp.h), self.keep.csr(pc.Mfp_s), self.keep.csr(fp.A10),
+                           C.pointer(self.kv.h) if cc else None)
         self.n = A.shape[0]
 
     def solve(self, b, rtol=1e-8, atol=0.0, max_it=100) -> CResult:

@@ -177,12 +177,13 @@ void oracle_amg_free(amg_t* H) {
 void oracle_amg_apply(const amg_t* H, const double* b, double* x) { cycle(H, 0, b, x); }
 
 /* 2-way block preconditioner with the pressure-Schur fieldsplit (split order f, p):
- *   y_s = K_s x_s ; t = x_fp - M_fps y_s ; y_f = K_f t_f ; y_p = K_p (t_p - A_pf y_f)        */
+ *   y_s = K_s x_s ; t = x_fp - M_fps y_s ; y_f = K_f t_f ; r = t_p - A_pf y_f ; y_p = K_p r  [+ K_v r  (SchurLowerCC)]   */
 typedef struct {
     int64_t ns, nf, np;
     const amg_t* Ks; const amg_t* Kf; const amg_t* Kp;
     csr_t Mfps;     /* (nf+np) x ns, may be empty */
     csr_t Apf;      /* np x nf */
+    const amg_t* Kv;     /* additive viscous part of the pressure Schur preconditioner, or NULL */
 } blockpc_t;
 
 static void blockpc_apply(const blockpc_t* M, const double* x, double* y, double* work) {
@@ -195,6 +196,13 @@ static void blockpc_apply(const blockpc_t* M, const double* x, double* y, double
     double* tp = work + nf + np;                /* np */
     residual(&M->Apf, y + ns, t + nf, tp);
     oracle_amg_apply(M->Kp, tp, y + ns + nf);
+    if (M->Kv) {
+        double* tv = tp + np;                   /* np */
+        oracle_amg_apply(M->Kv, tp, tv);
+        double* yp = y + ns + nf;
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < np; ++i) yp[i] += tv[i];
+    }
 }
 
 /* right-preconditioned GMRES, zero initial guess, restart = maxit (lib/Solver.py:99-100); returns iterations */
@@ -208,7 +216,7 @@ int oracle_gmres_right(const csr_t* A, const blockpc_t* M, const double* b, doub
     double* sn = (double*)calloc(m, sizeof(double));
     double* g = (double*)calloc(m + 1, sizeof(double));
     double* z = (double*)malloc((size_t)n * sizeof(double));
-    double* work = (double*)malloc((size_t)(M->nf + 2 * M->np + 8) * sizeof(double));
+    double* work = (double*)malloc((size_t)(M->nf + 3 * M->np + 8) * sizeof(double));
     double* h = (double*)malloc((size_t)(m + 1) * sizeof(double));
     memset(x, 0, (size_t)n * sizeof(double));
     double beta = sqrt(dot(n, b, b));

@@ -147,9 +147,15 @@ class Context:
     # --- options (PETSc.Options().setValue, lib/Parser.py:70-73)
     def set_option(self, key: str, val=None):
         check(self.lib.poro_options_set(self.h, key.encode(), None if val is None else str(val).encode()))
+        self.__dict__.setdefault("_options", {})[key.lstrip("-")] = val
+
+    def get_option(self, key: str, default=None):
+        """Host-side mirror of the options database (what set_option stored since the last clear_options)."""
+        return self.__dict__.get("_options", {}).get(key.lstrip("-"), default)
 
     def clear_options(self):
         check(self.lib.poro_options_clear(self.h))
+        self.__dict__["_options"] = {}
 
     def profile(self, enable=-1):
         """Phase profile {slot: (ms, calls)} from CUDA events (slots: see include/poro.h)."""

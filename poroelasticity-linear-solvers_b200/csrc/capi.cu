@@ -504,7 +504,6 @@ int poro_pc_setup(poro_ctx* h, poro_mat* A, poro_mat* P, poro_mat* P_diff, const
                   const char* inner_ksp_type_c, const char* inner_pc_type_c, const int64_t* bcs_sub_pressure, int64_t nbc,
                   int accel_order, double w1, double w2, poro_pc** out) {
     API_BEGIN
-    (void)A;
     Ctx& c = h->c;
     Fields& fl = h->fl;
     PORO_CUDA(cudaSetDevice(c.device));
@@ -598,6 +597,29 @@ int poro_pc_setup(poro_ctx* h, poro_mat* A, poro_mat* P, poro_mat* P_diff, const
             sch->A11 = extract_block(h, *Pp, fl.off[t1], fl.off[t1] + fl.n[t1], {t1});
             (t0 == 1 ? sch->A00 : sch->A11)->M.block_hint = bs_v;
             // selfp: S = A11 - A10 diag(A00)^-1 A01
+            // cc (extension): the diagonal is the lumped mass + drag part of the velocity block, mass_scale * |diag(A_fs)| of
+            // the SYSTEM matrix (A_fs = -(phi^2 / (k_f dt)) M_v with the rows of fluid Dirichlet dofs zeroed, which then get 1),
+            // and the viscous limit visc_scale * P_pp is added in the application (PCSchur::solve1); oracle: SchurLowerCC
+            const std::string sprec = c.opt("-fp_pc_fieldsplit_schur_precondition", "selfp");
+            PORO_REQUIRE(sprec == "selfp" || sprec == "cc", "-fp_pc_fieldsplit_schur_precondition must be selfp or cc");
+            DBuf<double> d_mass;
+            if (sprec == "cc") {
+                PORO_REQUIRE(!sch->p_first && pc_type == "diagonal", "schur_precondition cc needs pc type 'diagonal' and -fp_pc_fieldsplit_order fp");
+                PORO_REQUIRE(A != nullptr && c.has_opt("-fp_pc_fieldsplit_schur_cc_mass_scale") && c.has_opt("-fp_pc_fieldsplit_schur_cc_visc_scale"),
+                             "schur_precondition cc needs A and the -fp_pc_fieldsplit_schur_cc_mass_scale / _visc_scale options (lib/Preconditioner.py sets them)");
+                PORO_REQUIRE(ns == nf, "schur_precondition cc expects the displacement and velocity fields on the same nodes");
+                const double ms = c.opt_d("-fp_pc_fieldsplit_schur_cc_mass_scale", 0.0);
+                sch->visc_scale = c.opt_d("-fp_pc_fieldsplit_schur_cc_visc_scale", 0.0);
+                PORO_REQUIRE(ms > 0.0 && sch->visc_scale > 0.0, "schur_precondition cc: the two scales must be positive");
+                Csr Aperm;
+                const Csr* Ap = &A->raw;
+                if (!fl.identity) { permute_matrix(h, A->raw, Aperm); Ap = &Aperm; }
+                auto Afs = extract_block(h, *Ap, of, of + nf, {0});
+                d_mass.alloc((size_t)nf);
+                csr_diag(c, Afs->M, d_mass.p);
+                vec_abs_scale(c, d_mass.p, ms, nf);
+                PORO_CUDA(cudaStreamSynchronize(c.stream));
+            }
             DistPlan* plan0 = nullptr;
             DistPlan* plan1 = nullptr;
             if (c.nranks > 1 && c.opt_i("-poro_amg_distributed", 1)) { plan0 = sch->A00->plan_for_amg(); plan1 = sch->A11->plan_for_amg(); }
@@ -608,7 +630,7 @@ int poro_pc_setup(poro_ctx* h, poro_mat* A, poro_mat* P, poro_mat* P_diff, const
                 sch->S->ctx = &c;
                 sch->S->dplan = std::make_unique<DistPlan>();
                 dist_selfp_schur(c, *plan0, *plan1, sch->A00->mat(), sch->A01->mat(), sch->A10->mat(), sch->A11->mat(), sch->S->M,
-                                 *sch->S->dplan);
+                                 *sch->S->dplan, d_mass.p);
                 sch->S->n_owned_cols = sch->n1;
             } else
             // single rank (or -poro_amg_distributed 0): from the local (owned) parts
@@ -629,7 +651,8 @@ int poro_pc_setup(poro_ctx* h, poro_mat* A, poro_mat* P, poro_mat* P_diff, const
                 owned_cols(*sch->A10, (int)sch->n0, a10);
                 owned_cols(*sch->A11, (int)sch->n1, a11);
                 DBuf<double> dinv((size_t)sch->n0);
-                csr_diag(c, a00, dinv.p);
+                if (d_mass.p) PORO_CUDA(cudaMemcpy(dinv.p, d_mass.p, (size_t)sch->n0 * 8, cudaMemcpyDeviceToDevice));
+                else csr_diag(c, a00, dinv.p);
                 std::vector<double> hd((size_t)sch->n0);
                 PORO_CUDA(cudaMemcpy(hd.data(), dinv.p, hd.size() * 8, cudaMemcpyDeviceToHost));
                 for (auto& v : hd) v = v != 0.0 ? 1.0 / v : 1.0;
@@ -648,6 +671,11 @@ int poro_pc_setup(poro_ctx* h, poro_mat* A, poro_mat* P, poro_mat* P_diff, const
             // preconditioner built from the assembled selfp matrix
             sch->k1 = make_inner(h, sch->S.get(), "preonly", sub_pc, "fp_fieldsplit_1_", bs1, t1 == 1 ? cs : nullptr, t1 == 1 ? cdim : 0);
             sch->t0.alloc((size_t)sch->n0); sch->t1.alloc((size_t)sch->n1); sch->u0.alloc((size_t)sch->n0);
+            if (sprec == "cc") {
+                // Chebyshev(4) on the pressure mass matrix P_pp (scale-equivariant: the factor is applied to the result)
+                sch->kv = make_inner(h, sch->A11.get(), "preonly", "chebyshev", "fp_fieldsplit_1_visc_", 1, nullptr, 0);
+                sch->tv.alloc((size_t)sch->n1);
+            }
             cc.schur = sch.get();
             k->owned_pc = std::move(sch);
             k->pc = k->owned_pc.get();

@@ -254,6 +254,7 @@ struct Csr {
 void vec_copy(Ctx& c, double* y, const double* x, int64_t n);
 void vec_set(Ctx& c, double* y, double a, int64_t n);
 void vec_scale(Ctx& c, double* y, double a, int64_t n);
+void vec_abs_scale(Ctx& c, double* y, double a, int64_t n);                           // y = a |y|
 void vec_axpy(Ctx& c, double* y, double a, const double* x, int64_t n);             // y += a x
 void vec_aypx(Ctx& c, double* y, double a, const double* x, int64_t n);             // y = x + a y
 void vec_axpby(Ctx& c, double* y, double a, const double* x, double b, int64_t n);  // y = a x + b y

@@ -381,12 +381,13 @@ void dist_amg_level(Ctx& c, const Csr& A, const DistPlan& plan, const Csr& T, co
 
 // ---- exact selfp Schur complement of the owned rows -------------------------------------------------------------------
 void dist_selfp_schur(Ctx& c, DistPlan& plan0, DistPlan& plan1, const Csr& A00, const Csr& A01, const Csr& A10,
-                      const Csr& A11, Csr& S, DistPlan& planS) {
+                      const Csr& A11, Csr& S, DistPlan& planS, const double* diag0_owned) {
     const int n0 = plan0.n_owned, g0 = plan0.n_ghost;
     PORO_REQUIRE(A10.ncols == n0 + g0 && A01.nrows == n0, "Schur blocks and the halo plan of split 0 disagree");
     const int64_t N1 = plan1.offsets.back();
     DBuf<double> d((size_t)(n0 + g0));
-    csr_diag(c, A00, d.p);
+    if (diag0_owned) PORO_CUDA(cudaMemcpyAsync(d.p, diag0_owned, (size_t)n0 * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+    else csr_diag(c, A00, d.p);
     dist_halo_vec(c, plan0, d.p, 1, d.p + n0);
     { double* p = d.p; pfor(c, n0 + g0, [=] __device__(int64_t i) { p[i] = p[i] != 0.0 ? 1.0 / p[i] : 1.0; }); }
     Csr A01g, A01gh, A01ext, A10s, prod, A11g, Sg;

@@ -31,7 +31,8 @@ void dist_amg_level(Ctx& c, const Csr& A, const DistPlan& plan, const Csr& T, co
 // exact selfp Schur complement of the owned rows of split 1 (oracle/distamg_rank.py: dist_selfp_schur):
 //   S = A11 - A10 diag(A00)^-1 A01 with the A01 rows and the diagonal of the ghost dofs of split 0 exchanged.
 // plan0 / plan1: halo plans of the two splits (local columns of A00, A10 follow plan0; of A01, A11 plan1).
+// diag0_owned (optional): the diagonal to invert instead of diag(A00) (lumped mass + drag part of the velocity block, `cc`).
 void dist_selfp_schur(Ctx& c, DistPlan& plan0, DistPlan& plan1, const Csr& A00, const Csr& A01, const Csr& A10,
-                      const Csr& A11, Csr& S, DistPlan& planS);
+                      const Csr& A11, Csr& S, DistPlan& planS, const double* diag0_owned = nullptr);
 
 }  // namespace poro

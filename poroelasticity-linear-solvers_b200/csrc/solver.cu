@@ -568,6 +568,14 @@ void KSP::solve_cg(const double* b, double* x) {
 // =============================================================================================
 // fieldsplit Schur on the fp block
 // =============================================================================================
+void PCSchur::solve1(const double* r, double* y1) {
+    k1->solve(r, y1);
+    if (kv) {
+        kv->solve(r, tv.p);
+        vec_axpy(*ctx, y1, 1.0 / visc_scale, tv.p, n1);
+    }
+}
+
 void PCSchur::apply(const double* x, double* y) {
     Ctx& c = *ctx;
     const double* x0 = x + off0; const double* x1 = x + off1;
@@ -575,20 +583,20 @@ void PCSchur::apply(const double* x, double* y) {
     if (fact == 0) {                       // lower: y0 = K0 x0 ; y1 = K1 (x1 - A10 y0)
         { ProfScope ps(c, 3); k0->solve(x0, y0); }
         { ProfScope ps(c, 6); A10->apply(y0, t1.p, SPMV_SUB, x1); }
-        { ProfScope ps(c, 4); k1->solve(t1.p, y1); }
+        { ProfScope ps(c, 4); solve1(t1.p, y1); }
     } else if (fact == 1) {                // upper: y1 = K1 x1 ; y0 = K0 (x0 - A01 y1)
-        k1->solve(x1, y1);
+        solve1(x1, y1);
         A01->apply(y1, t0.p, SPMV_SUB, x0);
         k0->solve(t0.p, y0);
     } else if (fact == 2) {                // full: lower sweep then upper correction
         k0->solve(x0, u0.p);
         A10->apply(u0.p, t1.p, SPMV_SUB, x1);
-        k1->solve(t1.p, y1);
+        solve1(t1.p, y1);
         A01->apply(y1, t0.p, SPMV_SUB, x0);
         k0->solve(t0.p, y0);
     } else {                               // diag (PETSc flips the sign of the Schur block)
         k0->solve(x0, y0);
-        k1->solve(x1, y1);
+        solve1(x1, y1);
         vec_scale(c, y1, -1.0, n1);
     }
 }

@@ -146,7 +146,12 @@ struct PCSchur : PC {
     int64_t n0 = 0, n1 = 0, off0 = 0, off1 = 0;   // offsets inside the fp vector [f | p]
     std::unique_ptr<MatOp> A00, A01, A10, A11, S;
     std::unique_ptr<KSP> k0, k1;
-    DBuf<double> t0, t1, u0;
+    // `cc` (additive Cahouet-Chabard form, the pressure treatment of the reference's 3-way variants, lib/Assembler.py:131-137,
+    // inside the 2-way fieldsplit): y1 = K1(S_mass) r + (1 / visc_scale) Chebyshev(A11) r, S_visc = visc_scale * A11
+    std::unique_ptr<KSP> kv;
+    double visc_scale = 0.0;
+    DBuf<double> t0, t1, u0, tv;
+    void solve1(const double* r, double* y1);
     void apply(const double* x, double* y) override;
     const char* kind() const override { return "fieldsplit"; }
 };

@@ -39,6 +39,9 @@ void vec_set(Ctx& c, double* y, double a, int64_t n) {
 void vec_scale(Ctx& c, double* y, double a, int64_t n) {
     launch_elementwise(c, n, [=] __device__(int64_t i) { y[i] *= a; });
 }
+void vec_abs_scale(Ctx& c, double* y, double a, int64_t n) {
+    launch_elementwise(c, n, [=] __device__(int64_t i) { y[i] = a * fabs(y[i]); });
+}
 void vec_axpy(Ctx& c, double* y, double a, const double* x, int64_t n) {
     launch_elementwise(c, n, [=] __device__(int64_t i) { y[i] = fma(a, x[i], y[i]); });
 }

@@ -147,9 +147,26 @@ class _PC:
         return self._ctx_obj.h
 
 
+def cc_scales(parameters, dim):
+    """The two scalars of `-fp_pc_fieldsplit_schur_precondition cc` from the reference's parameter dict
+    (the coefficients of lib/Assembler.py:127-160, `diagonal` splitting):
+
+        mass_scale * |diag(A_fs)| = diag(c M_v),  A_fs = -(phi0^2 / (k_f dt)) M_v,  c = rho_f phi0 / dt + (1 + beta_f) phi0^2 / k_f
+        visc_scale * P_pp = (phi0 d / (2 mu_f)) M_p  (beta_CC1, lib/Assembler.py:131),  P_pp = (phi_s^2 / (k_s dt) + beta_p) M_p"""
+    phi0, dt, kf = float(parameters["phi0"]), float(parameters["dt"]), float(parameters["kf"])
+    phis = 1.0 - phi0
+    drag = phi0 ** 2 / kf
+    c = float(parameters["rhof"]) * phi0 / dt + (1.0 + float(parameters["betaf"])) * drag
+    beta_p = float(parameters["betap"]) * phis ** 2 / (dt * (2.0 * float(parameters["mu_s"]) / dim + float(parameters["lmbda"])))
+    mass_scale = c * dt / drag
+    visc_scale = (phi0 * dim / (2.0 * float(parameters["mu_f"]))) / (phis ** 2 / (float(parameters["ks"]) * dt) + beta_p)
+    return mass_scale, visc_scale
+
+
 class Preconditioner:
     def __init__(self, index_map, A, P, P_diff, parameters, bcs_sub_pressure):
         self.index_map = index_map
+        self.parameters = parameters
         self.A, self.P, self.P_diff = A, P, P_diff
         self.pc_type = parameters["pc type"]
         self.inner_ksp_type = parameters["inner ksp type"]
@@ -166,6 +183,15 @@ class Preconditioner:
 
     def get_pc(self):
         flag_3_way = self.pc_type in ("diagonal 3-way", "undrained 3-way")
+        lib_ctx = get_context()
+        if (self.pc_type == "diagonal" and lib_ctx.get_option("fp_pc_fieldsplit_schur_precondition") == "cc"
+                and lib_ctx.get_option("fp_pc_fieldsplit_schur_cc_mass_scale") is None):
+            dim = int(getattr(self.index_map, "block_dim", 0) or self.parameters.get("dim", 0))
+            if dim <= 0 and getattr(self.index_map, "coords_s", None) is not None:
+                dim = int(np.asarray(self.index_map.coords_s).shape[1])
+            ms, vs = cc_scales(self.parameters, dim)
+            lib_ctx.set_option("-fp_pc_fieldsplit_schur_cc_mass_scale", repr(ms))
+            lib_ctx.set_option("-fp_pc_fieldsplit_schur_cc_visc_scale", repr(vs))
         ctx = PreconditionerCC(self.P.mat(), self.P_diff.mat() if self.P_diff is not None else None, self.index_map,
                                flag_3_way, self.inner_ksp_type, self.inner_pc_type, self.inner_rtol, self.inner_atol,
                                self.inner_maxiter, self.inner_monitor, 1.0, 0.1, self.inner_accel_order,

@@ -30,6 +30,9 @@ for opt in os.environ.get("PORO_EXTRA_OPTIONS", "").split(";"):      # e.g. "-po
     if opt.strip():
         kv = opt.split()
         ctx.set_option(kv[0], kv[1] if len(kv) > 1 else None)
+CC = os.environ.get("PORO_WORKER_CC", "0") == "1"      # additive Cahouet-Chabard Schur preconditioner instead of selfp
+if CC:
+    ctx.set_option("-fp_pc_fieldsplit_schur_precondition", "cc")
 prob = distributed_problem(3, N, "diagonal", rank, world, ctx)
 s, par = prob.sys, dict(prob.par)
 par.update({"solver rtol": 1e-10, "solver atol": 0.0, "solver maxiter": 100})
@@ -64,7 +67,7 @@ twin_its = single_its = None
 if rank == 0:
     import scipy.sparse as sp
     from oracle.amg import SAAMG, rigid_body_modes
-    from oracle.blockpc import BlockPC, SchurLower, krylov_solver
+    from oracle.blockpc import BlockPC, SchurLower, SchurLowerCC, cc_from_matrices, krylov_solver
     from oracle.distamg import DistAmg
     from oracle.krylov import gmres
     from poro_b200.partition import slab_ranges
@@ -92,6 +95,11 @@ if rank == 0:
 
     def outer(mk_v, mk_p):
         mkfp = lambda M: SchurLower(M, glob.nf, glob.np_, krylov_solver("preonly", mk_v), krylov_solver("preonly", mk_p), "f")
+        if CC:
+            d_mass, S_visc = cc_from_matrices(glob, par)
+            cheb_p = lambda M: SAAMG(M, 1, None, max_levels=1, cheby_degree=4, dense_limit=0)
+            mkfp = lambda M: SchurLowerCC(M, glob.nf, glob.np_, krylov_solver("preonly", mk_v), krylov_solver("preonly", mk_p),
+                                          krylov_solver("preonly", cheb_p), d_mass, S_visc)
         pcg = BlockPC(glob, {"s": krylov_solver("preonly", mk_v), "fp": mkfp})
         return gmres(lambda v: glob.A @ v, glob.b, pcg, rtol=1e-10, atol=0.0, dtol=1e20, max_it=100, restart=100, pc_side="right")
 

@@ -29,15 +29,17 @@ def _bench_options():
 
 
 @pytest.mark.parametrize("N", [8, 16])
-def test_benchmarked_option_set_matches_cpu_twin(gpu_ctx, N):
-    """bench.py's configuration (s: V-cycle theta 0.04, f: Chebyshev(4), p: V-cycle on selfp S_p, split order fp)."""
+@pytest.mark.parametrize("which", ["bench", "selfp"])
+def test_benchmarked_option_set_matches_cpu_twin(gpu_ctx, N, which):
+    """bench.py's configuration (s, f: V-cycle theta 0.04; p: additive Cahouet-Chabard Schur preconditioner, split order fp) and
+    the PETSc-`selfp` set it replaced (f: Chebyshev(4), p: V-cycle on selfp S_p), each against its CPU twin."""
     import bench
     from oracle.problems import swelling
-    opts = _bench_options()
+    opts = _bench_options() if which == "bench" else bench.BENCH_OPTIONS_SELFP
     sys_, par = swelling(3, N, "diagonal")
     par = dict(par)
     par.update({"solver rtol": 1e-8, "solver atol": 0.0, "solver maxiter": 100, "solver type": "gmres"})
-    runs = bench.oracle_solver(sys_, par, 100)
+    runs = bench.oracle_solver(sys_, par, 100, opts)
     ro = runs["numpy/scipy, 1 thread"][0]()
     g = gpu_solve(sys_, par, opts)
     assert g["reason"] == 2 and ro.reason == 2
@@ -65,7 +67,8 @@ def test_chebyshev_pc_is_chebyshev_at_every_size(gpu_ctx):
     from oracle.problems import swelling
     from poro_b200.lib.backend import DeviceVector
     sys_, par = swelling(3, 3, "diagonal")            # f block: 3 * 7^3 = 1029 rows << 4096
-    g = gpu_solve(sys_, par, _bench_options(), return_objects=True)
+    import bench
+    g = gpu_solve(sys_, par, bench.BENCH_OPTIONS_SELFP, return_objects=True)
     cc = g["pc"].pc.getPythonContext()
     Pff = sp.csr_matrix(sys_.P)[sys_.is_f][:, sys_.is_f].tocsr()
     twin = SAAMG(Pff, 3, rigid_body_modes(sys_.coords_s, 3), max_levels=1, cheby_degree=4, dense_limit=0)
@@ -274,3 +277,40 @@ def test_optional_bsr_kernel_variants_are_the_same_operator(gpu_ctx, extra):
     assert alt["reason"] == ref["reason"] == 2
     assert alt["its"] == ref["its"]
     assert rel(alt["x"], ref["x"]) <= 1e-10
+
+
+@pytest.mark.parametrize("N", [8])
+def test_cc_schur_preconditioner_matches_cpu_twin(gpu_ctx, N):
+    """`-fp_pc_fieldsplit_schur_precondition cc` (additive Cahouet-Chabard form, the reference's 3-way pressure treatment inside
+    the 2-way fieldsplit) + V-cycle on the velocity block: the library derives the lumped mass from A_fs and the viscous limit
+    from P_pp with the two scalars lib/Preconditioner.py computes from the parameter dict; the CPU twin (oracle.blockpc.
+    SchurLowerCC) gets them from the same formulas.  Same iteration count (+-10 %), solution within 1e-8 of a direct solve."""
+    import bench
+    from oracle.problems import swelling
+    sys_, par = swelling(3, N, "diagonal")
+    par = dict(par)
+    par.update({"solver rtol": 1e-8, "solver atol": 0.0, "solver maxiter": 100, "solver type": "gmres"})
+    ro = bench.oracle_solver(sys_, par, 100, bench.BENCH_OPTIONS_CC)["numpy/scipy, 1 thread"][0]()
+    g = gpu_solve(sys_, par, bench.BENCH_OPTIONS_CC)
+    assert g["reason"] == 2 and ro.reason == 2
+    assert abs(g["its"] - ro.its) <= max(1, int(round(0.1 * ro.its))), (g["its"], ro.its)
+    res = np.linalg.norm(sys_.b - sys_.A @ g["x"]) / np.linalg.norm(sys_.b)
+    assert res <= 1.0e-8, res
+    assert rel(g["x"], ro.x) <= 1e-6
+    np.testing.assert_allclose(g["history"][:4], ro.history[:4], rtol=2e-2)
+    # the Schur matrix the library assembled is the twin's S_mass
+    cc = g["pc"].pc.getPythonContext() if hasattr(g["pc"], "pc") else None
+    if N == 8:
+        from oracle.blockpc import cc_from_matrices, submatrix
+        d_mass, _ = cc_from_matrices(sys_, par)
+        Pfp = sp.csr_matrix(sys_.P)
+        App, Apf, Afp = submatrix(Pfp, sys_.is_p, sys_.is_p), submatrix(Pfp, sys_.is_p, sys_.is_f), submatrix(Pfp, sys_.is_f, sys_.is_p)
+        S_twin = (App - Apf @ sp.diags(1.0 / d_mass) @ Afp).tocsr()
+        S_gpu = cc.block("schur")
+        assert abs(S_gpu - S_twin).max() <= 1e-12 * abs(S_twin).max()
+        par12 = dict(par)
+        par12["solver rtol"] = 1e-13
+        g12 = gpu_solve(sys_, par12, bench.BENCH_OPTIONS_CC)
+        xd = spla.spsolve(sys_.A.tocsc(), sys_.b)
+        assert g12["reason"] == 2
+        assert rel(g12["x"], xd) <= 1e-8, rel(g12["x"], xd)

@@ -56,3 +56,25 @@ def test_c_port_iteration_limit():
     sys_, _ = swelling(2, 8, "diagonal")
     got = cport.CSolver(sys_, _pc(sys_)).solve(sys_.b, 1e-14, 0.0, 3)
     assert got.its == 3 and got.reason == -3
+
+
+def test_c_solve_with_cahouet_chabard_schur_matches_numpy_and_the_scales_of_the_library():
+    """The benchmarked preconditioner: additive Cahouet-Chabard pressure Schur preconditioner (oracle.blockpc.SchurLowerCC).  The
+    two scalars lib/Preconditioner.py hands to the library reproduce the twin's lumped mass and viscous limit."""
+    import bench
+    from oracle.blockpc import cc_from_matrices, submatrix
+    from poro_b200.lib.Preconditioner import cc_scales
+    sys_, par = swelling(3, 4, "diagonal")
+    d_mass, S_visc = cc_from_matrices(sys_, par)
+    ms, vs = cc_scales(par, 3)
+    dm = np.abs(submatrix(sys_.A, sys_.is_f, sys_.is_s).diagonal()) * ms
+    np.testing.assert_allclose(np.where(dm > 0, dm, 1.0), d_mass, rtol=1e-14)
+    assert abs(vs * submatrix(sys_.P, sys_.is_p, sys_.is_p) - S_visc).max() <= 1e-14 * abs(S_visc).max()
+    runs = bench.oracle_solver(sys_, par, 100, bench.BENCH_OPTIONS)
+    ref = runs["numpy/scipy, 1 thread"][0]()
+    got = [r for k, (r, _) in runs.items() if k.startswith("C + OpenMP")][0]()
+    assert got.its == ref.its and got.reason == ref.reason == 2
+    np.testing.assert_allclose(got.x, ref.x, rtol=0, atol=1e-7 * np.abs(ref.x).max())
+    # and it is a different (better) preconditioner than selfp, not a relabelled one
+    selfp = bench.oracle_solver(sys_, par, 100, bench.BENCH_OPTIONS_SELFP)["numpy/scipy, 1 thread"][0]()
+    assert selfp.reason == 2 and ref.its <= selfp.its
