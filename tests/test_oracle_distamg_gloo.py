@@ -23,7 +23,7 @@ def _worker(rank, world, port, N, kw, q):
         from oracle.distamg import DistAmg
         from oracle.distamg_rank import Comm, RankAmg
         from oracle.problems import swelling
-        sys_, _ = swelling(3, N, "diagonal")
+        sys_, par = swelling(3, N, "diagonal")
         A = sp.csr_matrix(sys_.P)[sys_.is_s][:, sys_.is_s].tocsr()
         perm, off = _slab_perm(sys_.coords_s, N, world, 3)
         Ap = A[perm][:, perm].tocsr()
@@ -65,6 +65,14 @@ def _worker(rank, world, port, N, kw, q):
         assert abs(S_rows - S_ref).max() <= 1e-13 * abs(S_ref).max()
         S_owned_only = (App[pa:pb] - Apf[pa:pb, fa:fb] @ sp.diags(1.0 / Aff.diagonal()[fa:fb]) @ Afp[fa:fb]).tocsr()
         assert abs(S_owned_only - S_ref).max() > 1e-3 * abs(S_ref).max()      # what round 1 assembles is NOT the Schur complement
+        # the same exchange with the lumped mass + drag diagonal = the `cc` Schur matrix of the benchmarked option set
+        # (capi.cu hands `mass_scale |diag(A_fs)|` to dist_selfp_schur instead of diag(P_ff))
+        from oracle.blockpc import cc_from_matrices
+        d_mass = cc_from_matrices(sys_, par)[0][perm_f]
+        S_cc = dist_selfp_schur(comm, plan_f, Apf_loc, Afp[fa:fb], d_mass[fa:fb], App[pa:pb])
+        S_cc_ref = (App - Apf @ sp.diags(1.0 / d_mass) @ Afp).tocsr()[pa:pb]
+        assert abs(S_cc - S_cc_ref).max() <= 1e-13 * abs(S_cc_ref).max()
+        assert abs(S_cc_ref - S_ref).max() > 1e-3 * abs(S_ref).max()           # and it is not selfp under another name
         q.put((rank, "ok", len(mine.levels), comm.messages))
     except Exception:                                        # pragma: no cover
         import traceback
