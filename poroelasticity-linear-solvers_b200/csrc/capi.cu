@@ -694,6 +694,7 @@ int poro_pc_setup(poro_ctx* h, poro_mat* A, poro_mat* P, poro_mat* P_diff, const
                        cc.schur ? cc.schur->k0.get() : nullptr, cc.schur ? cc.schur->k1.get() : nullptr})
             if (k && k->type != "preonly") fixed = false;
         cc.graph_enabled = fixed && c.opt_i("-poro_pc_graph", 1) != 0;
+        cc.overlap_blocks = cc.graph_enabled && !cc.three_way && c.opt_i("-poro_pc_overlap_blocks", 1) != 0;
     }
     // the permuted copy of P is no longer needed
     pc->Pperm = Csr();

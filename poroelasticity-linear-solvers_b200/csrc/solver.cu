@@ -993,6 +993,23 @@ void PCBlockCC::apply_impl(const double* x, double* y) {
         vec_axpby(c, yp, w2, y_pd.p, w1, np);                               // :207-212
         vec_axpby(c, yf, w2, y_fd.p, w1, nf);
         vec_axpby(c, ys, w2, y_sd.p, w1, ns);
+    } else if (overlap_blocks && c.capture_log != nullptr && c.nranks <= 1 && Mfp_s->mat().nnz == 0 && Mfp_s->parts.empty()) {
+        // being captured: fork / join through events makes the two solves parallel branches of the graph
+        if (!side_stream) {
+            PORO_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+            PORO_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+            PORO_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        }
+        cudaStream_t main_stream = c.stream;
+        struct Restore { Ctx& c; cudaStream_t s; ~Restore() { c.stream = s; } } restore{c, main_stream};
+        PORO_CUDA(cudaEventRecord(ev_fork, main_stream));
+        PORO_CUDA(cudaStreamWaitEvent(side_stream, ev_fork, 0));
+        ksp_s->solve(xs, ys);                                               // :221
+        c.stream = side_stream;
+        ksp_fp->solve(xf, yf);                                              // :232-234 with P_fp,s = 0: t_fp = x_fp
+        PORO_CUDA(cudaEventRecord(ev_join, side_stream));
+        c.stream = main_stream;
+        PORO_CUDA(cudaStreamWaitEvent(main_stream, ev_join, 0));
     } else {
         {
             PhaseTimer t(c, timing, t_solid);

@@ -195,9 +195,21 @@ struct PCBlockCC : PC {
     DBuf<double> g_in, g_out;
     int64_t g_launches = 0;
     std::vector<KSP*> g_ksps;
+    // 2-way `diagonal` splitting: P_fp,s is structurally empty, so the solid solve and the fluid-pressure solve are independent.
+    // Inside the captured graph they are forked onto two streams (two parallel branches of the graph): the latency-bound
+    // coarse levels of one hierarchy run under the bandwidth-bound level-0 launches of the other.  Single rank only: the
+    // distributed coarse solves share one peer-store all-reduce channel whose use must stay ordered across ranks.
+    bool overlap_blocks = false;
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     void apply(const double* x, double* y) override;
     void apply_impl(const double* x, double* y);
-    ~PCBlockCC() override { if (gexec) cudaGraphExecDestroy(gexec); }
+    ~PCBlockCC() override {
+        if (gexec) cudaGraphExecDestroy(gexec);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (side_stream) cudaStreamDestroy(side_stream);
+    }
     const char* kind() const override { return "blockcc"; }
 };
 
