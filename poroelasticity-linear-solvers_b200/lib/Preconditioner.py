@@ -189,7 +189,12 @@ class Preconditioner:
             dim = int(getattr(self.index_map, "block_dim", 0) or self.parameters.get("dim", 0))
             if dim <= 0 and getattr(self.index_map, "coords_s", None) is not None:
                 dim = int(np.asarray(self.index_map.coords_s).shape[1])
-            ms, vs = cc_scales(self.parameters, dim)
+            try:
+                ms, vs = cc_scales(self.parameters, dim)
+            except (KeyError, ZeroDivisionError) as e:
+                raise ValueError("-fp_pc_fieldsplit_schur_precondition cc needs the physical parameters of the reference's "
+                                 "parameter dict (phi0, dt, kf, ks, rhof, mu_f, mu_s, lmbda, betaf, betap) and the space "
+                                 "dimension, or explicit -fp_pc_fieldsplit_schur_cc_mass_scale / _visc_scale options: %r" % (e,))
             lib_ctx.set_option("-fp_pc_fieldsplit_schur_cc_mass_scale", repr(ms))
             lib_ctx.set_option("-fp_pc_fieldsplit_schur_cc_visc_scale", repr(vs))
         ctx = PreconditionerCC(self.P.mat(), self.P_diff.mat() if self.P_diff is not None else None, self.index_map,
