@@ -263,10 +263,12 @@ def test_fp32_storage_of_preconditioner_matrices_is_only_a_preconditioner_change
     assert rel(g32["x"], g64["x"]) <= 1e-8
 
 
-@pytest.mark.parametrize("extra", ["-poro_bsr_coop_gather 1", "-poro_bsr_l2_prefetch_chunks 4", "-poro_bsr_tma 1"])
+@pytest.mark.parametrize("extra", ["-poro_bsr_coop_gather 1", "-poro_bsr_l2_prefetch_chunks 4", "-poro_bsr_tma 1",
+                                   "-poro_pc_overlap_blocks 0", "-poro_pc_graph 0"])
 def test_optional_bsr_kernel_variants_are_the_same_operator(gpu_ctx, extra):
     """The measured-and-rejected kernel variants (profiles/r2_bsr_kernels.md) stay selectable; they must be the same linear
-    operators as the default kernel: same iteration count, same solution."""
+    operators as the default kernel: same iteration count, same solution.  Likewise the scheduling switches: the solid and
+    the fluid-pressure solve as a chain instead of two parallel graph branches, and eager launches instead of the graph."""
     import bench
     from oracle.problems import swelling
     sys_, par = swelling(3, 8, "diagonal")
